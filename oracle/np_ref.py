@@ -1,0 +1,70 @@
+"""Independent fp64 numpy/scipy restatements of the two core contractions — TEST INFRASTRUCTURE ONLY.
+
+Used to cross-check `oracle/sgformer_oracle.py` (and through it the CUDA kernels) against arithmetic
+that shares no code with torch: plain einsum for the linear attention (medium/ours.py:14-34) and
+scipy CSR for Â·X (large/ours.py:25-34).  See the header of sgformer_oracle.py for who may import oracle/.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+
+def attention_fp64(q, k, v):
+    """q,k [N,H,M], v [N,H,D] -> dict(out [N,H,D], S' [H,M,D], z' [H,M], nq2, nk2) in float64."""
+    q, k, v = (np.asarray(t, dtype=np.float64) for t in (q, k, v))
+    n = q.shape[0]
+    nq2, nk2 = float((q * q).sum()), float((k * k).sum())
+    s_raw = np.einsum("lhm,lhd->hmd", k, v)
+    z_raw = k.sum(axis=0)
+    qn = q / np.sqrt(nq2)
+    num = np.einsum("nhm,hmd->nhd", qn, s_raw / np.sqrt(nk2)) + n * v
+    den = np.einsum("nhm,hm->nh", qn, z_raw / np.sqrt(nk2)) + n
+    return dict(out=num / den[..., None], S=s_raw, z=z_raw, nq2=nq2, nk2=nk2)
+
+
+def attention_grads_fp64(q, k, v, g):
+    """Closed-form backward of `attention_fp64`; g = dL/dout [N,H,D]."""
+    q, k, v, g = (np.asarray(t, dtype=np.float64) for t in (q, k, v, g))
+    n = q.shape[0]
+    nq, nk = np.sqrt((q * q).sum()), np.sqrt((k * k).sum())
+    qn, kn = q / nq, k / nk
+    s = np.einsum("lhm,lhd->hmd", kn, v)
+    z = kn.sum(axis=0)
+    num = np.einsum("nhm,hmd->nhd", qn, s) + n * v
+    den = np.einsum("nhm,hm->nh", qn, z) + n
+    o = num / den[..., None]
+    gnum = g / den[..., None]
+    gden = -(g * o).sum(-1) / den
+    ds = np.einsum("nhm,nhd->hmd", qn, gnum)
+    dz = np.einsum("nhm,nh->hm", qn, gden)
+    dqn = np.einsum("nhd,hmd->nhm", gnum, s) + gden[..., None] * z[None]
+    dv = n * gnum + np.einsum("nhm,hmd->nhd", kn, ds)
+    dkn = np.einsum("nhd,hmd->nhm", v, ds) + dz[None]
+    dq = (dqn - qn * (dqn * qn).sum()) / nq
+    dk = (dkn - kn * (dkn * kn).sum()) / nk
+    return dict(dq=dq, dk=dk, dv=dv, dS=ds, dz=dz)
+
+
+def gcn_csr(edge_index, n):
+    """Canonical CSR of the aggregation pattern: row index = edge target (`col`), column index = edge
+    source (`row`), entries sorted by (target, source), duplicates kept (torch_sparse SparseTensor
+    semantics).  Returns rowptr int64 [n+1], col int32 [nnz], dinv float32 [n]."""
+    src = np.asarray(edge_index[0], dtype=np.int64)
+    dst = np.asarray(edge_index[1], dtype=np.int64)
+    order = np.lexsort((src, dst))
+    deg = np.bincount(dst, minlength=n)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    with np.errstate(divide="ignore"):
+        dinv = np.where(deg > 0, 1.0 / np.sqrt(deg.astype(np.float64)), 0.0).astype(np.float32)
+    return rowptr, src[order].astype(np.int32), dinv
+
+
+def spmm_fp64(edge_index, n, x):
+    """y = D^-1/2 A D^-1/2 x in float64 through scipy (duplicates summed == counted)."""
+    src = np.asarray(edge_index[0], dtype=np.int64)
+    dst = np.asarray(edge_index[1], dtype=np.int64)
+    deg = np.bincount(dst, minlength=n).astype(np.float64)
+    with np.errstate(divide="ignore"):
+        dinv = np.where(deg > 0, 1.0 / np.sqrt(deg), 0.0)
+    a = sp.coo_matrix((dinv[dst] * dinv[src], (dst, src)), shape=(n, n)).tocsr()
+    return a @ np.asarray(x, dtype=np.float64)

@@ -1,0 +1,3 @@
+class Data:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
