@@ -1,0 +1,232 @@
+/* sgformer_b200 — C-ABI of the B200 (sm_100a) SGFormer encoder hot path.
+ *
+ * The reference (qitianwu/SGFormer) has no FFI: its hot path is `ours.py` calling torch / torch_sparse /
+ * torch_geometric ops.  Each entry point below replaces one of those call sites (cited per function,
+ * paths relative to the reference root).  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory unless marked host;
+ *   - `stream` is a cudaStream_t passed as void*; launchers never synchronise and never allocate
+ *     (workspaces are passed in; *_ws_bytes tells the size);
+ *   - return 0 on success, a positive cudaError_t, or a negative SGF_ERR_* argument error;
+ *   - dtype codes: SGF_F32 = 0 (float), SGF_BF16 = 1 (__nv_bfloat16); matrices are row-major with an
+ *     explicit leading dimension in ELEMENTS; feature rows must be 16-byte aligned and have a
+ *     16-byte-multiple pitch;
+ *   - node ids fit int32; rowptr is int64 (nnz of a papers100M-scale graph exceeds 2^31).
+ * There is no CPU implementation behind this header and no fallback: without a CUDA device every
+ * compute entry point fails with the CUDA error.
+ */
+#ifndef SGFORMER_B200_H
+#define SGFORMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGF_F32 0
+#define SGF_BF16 1
+
+#define SGF_ERR_ARG (-1)
+#define SGF_ERR_UNSUPPORTED (-2)
+#define SGF_ERR_DRIVER (-3)
+
+/* library / build info: "sgformer_b200 <version> sm_100a" (host string, static storage) */
+const char* sgf_version(void);
+/* number of kernels this library has launched since load (host counter; bench.py's gpu_launches) */
+int64_t sgf_launch_count(void);
+/* select the CUDA device for subsequent launches of the calling thread (the library carries its own static CUDA
+ * runtime; the host framework's cudaSetDevice does not reach it).  Returns a cudaError_t. */
+int sgf_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 — graph structure (replaces, per GraphConvLayer.forward call, large/ours.py:26-33:
+ *   PyG degree() + per-edge weights + torch_sparse.SparseTensor(row=col, col=row) i.e. argsort of
+ *   target*N+source and rowptr build; hoisted here to once per graph).
+ * Builds the CSR of the aggregation pattern: by_source = 0 -> rows = edge targets (edge_index[1]),
+ * columns = sources; by_source = 1 -> the transpose (used by the backward, large/ours.py autograd of :34).
+ * Entries of a row are sorted by column, duplicates kept  => rowptr/col are bit-exact with the
+ * reference's SparseTensor storage.
+ * self_loop_mode 0: edges as given (large/100M GraphConv).  1: PyG gcn_norm semantics
+ * (medium/models.py:22-37 GCNConv): existing self loops dropped, one self loop per node added.
+ * dinv (nullable, by_source = 0 only): dinv[i] = sqrt(1/len(row i)) or 0 for empty rows
+ * (== (1/d).sqrt() with nan_to_num -> 0, large/ours.py:29-32).
+ * col must hold nnz (+ n when self_loop_mode = 1) entries; the true count is rowptr[n].
+ * ------------------------------------------------------------------------------------------------ */
+int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes /* host out */);
+int sgf_csr_build(const int64_t* edge_index /* [2,nnz] */, int64_t nnz, int64_t n, int by_source,
+                  int self_loop_mode, int64_t* rowptr /* [n+1] */, int32_t* col, float* dinv /* [n] or NULL */,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* K9 — induced subgraph with relabelling (replaces PyG subgraph(idx, edge_index, num_nodes=n,
+ * relabel_nodes=True) at large/main-batch.py:139 / large/eval.py:89): keeps edges whose endpoints are
+ * both in `subset` and maps node ids to positions in `subset`.  Output order = input edge order
+ * (bit-exact with the reference).  node_map: int32 [n] workspace; out_count: device int64 scalar. */
+int sgf_subgraph(const int64_t* edge_index, int64_t nnz, int64_t n, const int64_t* subset, int64_t n_sub,
+                 int32_t* node_map, int64_t* out_edge_index /* [2,nnz] capacity, pitch nnz */,
+                 int64_t* out_count, void* ws, size_t ws_bytes, void* stream);
+int sgf_subgraph_ws_bytes(int64_t nnz, int64_t n, size_t* bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6 / K7 — CSR SpMM (replaces torch_sparse.matmul(adj, x), large/ours.py:34, 100M/ours.py:80, and its
+ * autograd transpose):  y[r,:] = row_scale[r] * sum_{j in row r} x[col[j], :]   (row_scale nullable).
+ * Â = D^-1/2 A D^-1/2 is applied as: producer pre-scales x rows by dinv, row_scale = dinv.
+ * out_scaled (nullable): second output out_scaled[r,:] = row_scale[r] * y[r,:] is NOT written here.
+ * Pure HBM-bound gather: 128-bit loads of neighbour rows, fp32 accumulation, no tensor cores.
+ * ------------------------------------------------------------------------------------------------ */
+int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
+             void* y, int64_t ldy, int64_t n_rows, int h, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contractions on tcgen05 tensor cores (bf16 operands staged by TMA, fp32 accumulation in TMEM).
+ * Replace nn.Linear / torch.einsum call sites (medium/ours.py:21-22,27-28,76-85; large/ours.py:38-40,
+ * 123-128,136-143,199,275).
+ * ------------------------------------------------------------------------------------------------ */
+#define SGF_MAX_SRC 4
+#define SGF_MAX_SEG 16
+
+/* out = epilogue( sum_s A[seg_a[s]][:, koff:koff+klen] . B[seg_b[s]][:, koff:koff+klen]^T )
+ * A[i]: bf16 [rows, a_cols[i]] (K-major), B[i]: bf16 [n_out, b_cols[i]] (K-major, e.g. an nn.Linear weight).
+ * When seg_klen is not a multiple of 64 the A columns [koff+klen, next multiple of 64) must be zero (zero padding, or
+ * the end of the tensor where TMA zero-fills) and the B columns there finite.
+ * Optional tail: 16 extra output columns whose B rows come from b_tail [16, b_cols] (bf16), only with a
+ * single B source; used for the attention normaliser column.  n_out (+16) <= 272 per n-block of 256. */
+#define SGF_EPI_AFFINE 0      /* out = (alpha*acc + beta*aux[r,c] + bias[c] + r1_row[r]*r1_col[c]) -> relu -> *row_scale[r] (+= out) */
+#define SGF_EPI_ATTN_APPLY 1  /* out[r,c] = (acc[r,c] + nf*aux[r,c]) / (acc_tail[r,0] + nf); den_out[r] = that denominator */
+
+typedef struct {
+    const void* a[SGF_MAX_SRC]; int64_t lda[SGF_MAX_SRC]; int64_t a_cols[SGF_MAX_SRC];
+    const void* b[SGF_MAX_SRC]; int64_t ldb[SGF_MAX_SRC]; int64_t b_cols[SGF_MAX_SRC];
+    int32_t n_a, n_b, n_seg;
+    int32_t seg_a[SGF_MAX_SEG], seg_akoff[SGF_MAX_SEG], seg_b[SGF_MAX_SEG], seg_bkoff[SGF_MAX_SEG], seg_klen[SGF_MAX_SEG];
+    const void* b_tail; int64_t ldb_tail;      /* NULL = no tail */
+    int64_t rows; int32_t n_out;
+    /* epilogue */
+    int32_t epi;
+    void* out; int64_t ldo; int32_t out_dtype;
+    const float* bias;                          /* [n_out] or NULL */
+    const void* aux; int64_t ld_aux; int32_t aux_dtype;   /* [rows, n_out] or NULL */
+    const float* row_scale;                     /* [rows] or NULL */
+    float alpha, beta;                          /* host scalars */
+    const float* alpha_dev; const float* beta_dev; /* optional device scalars multiplied into alpha/beta */
+    int32_t relu, accumulate;
+    float nf;                                   /* ATTN_APPLY: node count N as float */
+    float* den_out;                             /* ATTN_APPLY: [rows] fp32 or NULL */
+    const float* r1_row; const float* r1_col;   /* AFFINE: optional rank-1 term + r1_row[r]*r1_col[c] (both or neither) */
+} sgf_gemm_nt_args;
+int sgf_gemm_nt(const sgf_gemm_nt_args* args /* host */, void* stream);
+
+/* Node-contracting product: out[M,N] = alpha * sum_n A[n,:M]^T B[n,:N]  (+ beta*out), fp32 output.
+ * A: bf16 [rows, m] row-major, B: bf16 [rows, n] row-major; m <= 256, n <= 256.
+ * Used for K^T V (medium/ours.py:21), q^T gnum (its backward) and every weight gradient dW = dY^T X.
+ * Deterministic two-stage reduction through `ws` (sgf_gemm_tn_ws_bytes).  transpose_out writes out[N,M]. */
+typedef struct {
+    const void* a; int64_t lda; int32_t m;
+    const void* b; int64_t ldb; int32_t n;
+    int64_t rows;
+    float* out; int64_t ldo; int32_t transpose_out;
+    float alpha, beta; const float* alpha_dev;
+    void* ws; size_t ws_bytes;
+} sgf_gemm_tn_args;
+int sgf_gemm_tn_ws_bytes(int32_t m, int32_t n, int64_t rows, size_t* bytes);
+int sgf_gemm_tn(const sgf_gemm_tn_args* args /* host */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-streaming kernels (replace the ATen elementwise / reduction passes: torch.norm medium/ours.py:16-17,
+ * nn.LayerNorm, nn.BatchNorm1d, F.relu, F.dropout, residual mixes large/ours.py:79-93,199-216,270).
+ * All take dtype in {SGF_F32, SGF_BF16} for the [rows,h] activations; statistics/parameters are fp32.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* column statistics: sum[c] += w[r]*x[r,c], sumsq[c] += x[r,c]^2 (outputs must be zeroed by the caller;
+ * sum, sumsq, w nullable).  Gives K^T 1, ||Q||^2, ||K||^2, q^T gden, BatchNorm batch statistics. */
+int sgf_colstats(const void* x, int64_t ldx, int64_t rows, int h, int dtype, const float* w,
+                 float* sum, float* sumsq, void* stream);
+
+/* y = dropout( relu?( LN?( a*x + b*r ) ) ), r nullable.  stats: fp32 [rows,2] (mean, rstd) or NULL.
+ * (TransConv.forward, large/ours.py:199-216).  p = dropout prob, seed identifies the mask. */
+int sgf_ln_fwd(const void* x, const void* r, int64_t ld, int64_t rows, int h, int dtype, float a, float b,
+               const float* gamma, const float* beta, int use_ln, int use_relu, float p, uint64_t seed,
+               void* y, float* stats, void* stream);
+/* backward of sgf_ln_fwd for the upstream gradient gscale*dy: writes dx = a*du and (if dr != NULL) dr = b*du;
+ * accumulates dgamma[c], dbeta[c] (fp32, caller-zeroed, nullable when !use_ln). */
+int sgf_ln_bwd(const void* dy, const void* x, const void* r, int64_t ld, int64_t rows, int h, int dtype,
+               float a, float b, const float* gamma, const float* beta, const float* stats, int use_ln,
+               int use_relu, float p, uint64_t seed, float gscale, void* dx, void* dr, float* dgamma, float* dbeta,
+               void* stream);
+
+/* BatchNorm1d (+bias +ReLU +dropout +residual +branch mix) — GraphConv.forward large/ours.py:78-93, GCN.forward
+ * medium/models.py:49-63, SGFormer.forward large/ours.py:270.
+ * sgf_bn_finalize: batch statistics from column sums of z (training; sum/sumsq non-NULL; updates the running buffers
+ * with momentum and the unbiased variance when they are non-NULL) or the running statistics (sum == NULL).  zbias
+ * (nullable) is a per-column bias added to z before normalisation (GCNConv's bias): it only shifts the mean.
+ * sgf_bn_fwd:  t = use_bn ? gamma*((z+zbias)-mean)*rstd+beta : z+zbias;  t = relu?(t);  t = dropout(t);  t += res?;
+ *   y_scaled (nullable) = row_scale[r]*t;   if mix: t = gw*t + (1-gw)*mix[r,:];   y (nullable) = t. */
+int sgf_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int h, float eps, float momentum,
+                    const float* zbias, float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+int sgf_bn_fwd(const void* z, const void* res, const void* mix, int64_t ld, int64_t rows, int h, int dtype,
+               const float* mean, const float* rstd, const float* gamma, const float* beta, const float* zbias,
+               int use_bn, int use_relu, float p, uint64_t seed, float gw, const float* row_scale, void* y,
+               void* y_scaled, void* stream);
+/* backward.  Upstream gradient g_raw = gscale*(dy + row_scale2[r]*dy2) (dy or dy2 nullable, not both);
+ * g = g_raw * dropout mask * relu mask.
+ * phase 1 (training BN only): sums[0:h] += g, sums[h:2h] += g*xhat   (caller-zeroed fp32 [2h]; == dbeta, dgamma)
+ * phase 2: dz = gamma*rstd*(g - sums_g/rows - xhat*sums_gx/rows) (training BN) | gamma*rstd*g (eval BN) | g (no BN);
+ *   dz is written times out_row_scale[r] (nullable); dz_colsum[c] += dz (unscaled; bias gradient; nullable);
+ *   dres (nullable) = or += g_raw (gradient of the residual input). */
+int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld,
+                      int64_t rows, int h, int dtype, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, const float* zbias, int use_bn, int use_relu, float p, uint64_t seed,
+                      float gscale, float* sums, void* stream);
+int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld,
+                     int64_t rows, int h, int dtype, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, const float* zbias, int use_bn, int use_relu, int training, float p,
+                     uint64_t seed, float gscale, const float* sums, void* dz, void* dres, int dres_accumulate,
+                     float* dz_colsum, const float* out_row_scale, void* stream);
+
+/* out = (a*x + b*y) * row_scale[r]  (y, row_scale nullable; y has x's dtype); in/out dtypes may differ (casts). */
+int sgf_axpby(const void* x, int64_t ldx, int x_dtype, const void* y, int64_t ldy, int y_dtype, float a, float b,
+              const float* row_scale, void* out, int64_t ldo, int out_dtype, int64_t rows, int h, void* stream);
+/* fp32 [rows, cols] -> bf16 tensor-core operand dst (optionally transposed: dst[c, r] = src[r, c]) whose K extent is
+ * zero-padded to kp; plane_ld = 0: one bf16 plane; plane_ld >= kp: three planes side by side along K with
+ * src ~= p0 + p1 + p2 (bf16x3 split: fp32-accurate products on the bf16 tensor cores).  colsum (nullable, caller-zeroed):
+ * exact fp32 column sums of src (bias gradients). */
+int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, int cols, int transpose, void* dst,
+                     int64_t ld_dst, int kp, int64_t plane_ld, float* colsum, void* stream);
+/* mean over heads: out[r,c] = (1/heads) * sum_h x[r, h*d + c]  (TransConvLayer, medium/ours.py:95) */
+int sgf_head_mean(const void* x, int64_t ldx, int64_t rows, int heads, int d, int dtype, void* out, int64_t ldo,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Linear attention glue (full_attention_conv, medium/ours.py:14-34; backward per SURVEY.md Appendix A.1)
+ * ------------------------------------------------------------------------------------------------ */
+/* Operand format of the small bf16 matrices written by the prepare kernels: plane_ld = 0 -> one bf16 plane;
+ * plane_ld > 0 -> three planes side by side along K (value ~= p0+p1+p2, see sgf_split3) for fp32-accurate GEMMs.
+ *
+ * sgf_attn_prepare_fwd: from the pass-1 partials S'[m,d] = k^T v (sgf_gemm_tn), z'[m] = k^T 1 and the per-column
+ * sums of squares of q and k (sgf_colstats; nq2 = sum(nq2v), nk2 = sum(nk2v)) build the B operands of the apply GEMM:
+ *   bmat[d, m] = S'[m,d]/(nq*nk) (K-major over m), btail[0, m] = z'[m]/(nq*nk), btail[1..15,:] = 0;
+ *   scal[0] = 1/nq, scal[1] = 1/nk, scal[2] = 1/(nq*nk). */
+int sgf_attn_prepare_fwd(const float* s_raw, const float* z_raw, const float* nq2v, int nq2_len, const float* nk2v,
+                         int nk2_len, int m, int d, void* bmat, int64_t ld_bmat, void* btail, int64_t ld_btail,
+                         int64_t plane_ld, float* scal, void* stream);
+/* gnum = gscale*g/den, gden = -gscale*(g.o)/den  (per row); gnum: [rows,d] same dtype as g, gden: fp32 [rows] */
+int sgf_attn_bwd_prep(const void* g, int64_t ld, const void* o, int64_t ld_o, const float* den, int64_t rows, int d,
+                      int dtype, float gscale, void* gnum, int64_t ld_gnum, float* gden, void* stream);
+/* multi-head: the norm-gradient scalar c is shared by all heads; sums scal_bwd[i*stride+3] and rewrites entries 1,2 */
+int sgf_attn_combine_scal(float* scal_bwd, int heads, int stride, const float* scal_fwd, void* stream);
+/* Backward glue (SURVEY.md Appendix A.1 rewritten for raw q,k): with alpha = 1/(nq*nk), dS_raw = q^T gnum,
+ * dz_raw = q^T gden:  b_dq[m,d] = S'[m,d], b_dk[m,d] = dS_raw[m,d], b_dv[d,m] = dS_raw[m,d],
+ * r1_col[m] = alpha*z'[m], dk_bias[m] = alpha*dz_raw[m], c = alpha*(<dS_raw,S'> + <dz_raw,z'>),
+ * scal_bwd = {alpha, -c/nq^2, -c/nk^2, c}.  Then
+ *   dq = alpha*(gnum.b_dq^T) + gden (x) r1_col + scal_bwd[1]*q
+ *   dk = alpha*(v.b_dk^T) + dk_bias + scal_bwd[2]*k
+ *   dv = alpha*(k.b_dv^T) + N*gnum */
+int sgf_attn_prepare_bwd(const float* s_raw, const float* z_raw, const float* ds_raw, const float* dz_raw,
+                         const float* scal_fwd, int m, int d, void* b_dq, int64_t ld_b_dq, void* b_dv, int64_t ld_b_dv,
+                         void* b_dk, int64_t ld_b_dk, int64_t plane_ld_d, int64_t plane_ld_m, float* r1_col,
+                         float* dk_bias, float* scal_bwd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGFORMER_B200_H */

@@ -1,0 +1,483 @@
+// K5 — CSR / CSC build of the GCN aggregation pattern, and K9 — induced subgraph with relabelling.
+//
+// Reference behaviour replaced (per call, /root/reference): large/ours.py:26-33 (PyG degree -> edge weights ->
+// torch_sparse.SparseTensor(row=col, col=row): argsort of target*N+source + rowptr), medium/models.py:22-37
+// (PyG gcn_norm: add_remaining_self_loops + degree), large/main-batch.py:139 (PyG subgraph, CPU, O(E) per batch).
+//
+// Pipeline (all HBM-bound integer work, no tensor cores):
+//   count   : one pass over the int64 edge list, atomicAdd into int32 row counters        (8 B/edge read)
+//   scan    : 3-kernel exclusive scan of the counters -> int64 rowptr                       (12 B/node)
+//   fill    : second pass, cursor atomics, writes int32 column ids                          (16 B/edge read, 4 B write)
+//   sort    : per-row sort of the column ids (warp rank-sort <=32, block bitonic in smem <=2048, block bitonic
+//             in global memory above) so the arrays are deterministic and bit-exact with the reference's
+//             (target, source)-sorted storage
+//   dinv    : dinv[i] = sqrt(1/len_i) (0 for empty rows)
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/sgformer_b200.h"
+
+namespace sgf {
+
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;  // per thread -> 4096 per block
+
+__global__ void csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+                                 int64_t n, int drop_self_loops, int* __restrict__ counts, int* __restrict__ err) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        int64_t k = key[e], v = val[e];
+        if (k < 0 || k >= n || v < 0 || v >= n) { atomicExch(err, 1); continue; }
+        if (drop_self_loops && k == v) continue;
+        atomicAdd(&counts[k], 1);
+    }
+}
+
+// counts[i] (+1 if add_loop) -> block-local exclusive scan into rowptr[i]; block totals to block_sums
+__global__ void scan_local_kernel(const int* __restrict__ counts, int64_t n, int add_loop, int64_t* __restrict__ rowptr,
+                                  int64_t* __restrict__ block_sums) {
+    __shared__ int64_t warp_tot[32];
+    const int tid = threadIdx.x;
+    const int64_t base = ((int64_t)blockIdx.x * kScanBlock + tid) * kScanItems;
+    int64_t v[kScanItems];
+    int64_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t idx = base + i;
+        v[i] = idx < n ? (int64_t)counts[idx] + add_loop : 0;
+        tsum += v[i];
+    }
+    // inclusive warp scan of tsum
+    int64_t x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((tid & 31) >= o) x += y;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = x;
+    __syncthreads();
+    if (tid < 32) {
+        int64_t w = warp_tot[tid];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (tid >= o) w += y;
+        }
+        warp_tot[tid] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int64_t excl = x - tsum + ((tid >> 5) > 0 ? warp_tot[(tid >> 5) - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t idx = base + i;
+        if (idx < n) rowptr[idx] = excl;
+        excl += v[i];
+    }
+    if (tid == kScanBlock - 1) block_sums[blockIdx.x] = warp_tot[31];
+}
+
+// single block: exclusive scan of block_sums in place; total -> *total_out
+__global__ void scan_block_sums_kernel(int64_t* __restrict__ block_sums, int64_t nblocks, int64_t* __restrict__ total_out) {
+    __shared__ int64_t warp_tot[32];
+    __shared__ int64_t carry_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nblocks; base += kScanBlock) {
+        int64_t idx = base + tid;
+        int64_t v = idx < nblocks ? block_sums[idx] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = x;
+        __syncthreads();
+        if (tid < 32) {
+            int64_t w = warp_tot[tid];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (tid >= o) w += y;
+            }
+            warp_tot[tid] = w;
+        }
+        __syncthreads();
+        int64_t carry = carry_s;
+        int64_t excl = carry + x - v + ((tid >> 5) > 0 ? warp_tot[(tid >> 5) - 1] : 0);
+        if (idx < nblocks) block_sums[idx] = excl;
+        __syncthreads();
+        if (tid == 0) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) *total_out = carry_s;
+}
+
+__global__ void scan_add_kernel(int64_t* __restrict__ rowptr, int64_t n, const int64_t* __restrict__ block_sums,
+                                const int64_t* __restrict__ total, int* __restrict__ cursor, int add_loop) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        if (i == n) { rowptr[n] = *total; continue; }
+        rowptr[i] += block_sums[i / (kScanBlock * kScanItems)];
+        cursor[i] = 0;
+    }
+}
+
+__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz, int64_t n,
+                                int drop_self_loops, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
+                                int32_t* __restrict__ col) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        int64_t k = key[e], v = val[e];
+        if (k < 0 || k >= n || v < 0 || v >= n) continue;
+        if (drop_self_loops && k == v) continue;
+        int pos = atomicAdd(&cursor[k], 1);
+        col[rowptr[k] + pos] = (int32_t)v;
+    }
+}
+
+__global__ void csr_add_loops_kernel(int64_t n, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
+                                     int32_t* __restrict__ col) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int pos = atomicAdd(&cursor[i], 1);
+        col[rowptr[i] + pos] = (int32_t)i;
+    }
+}
+
+// ---- per-row sort ---------------------------------------------------------------------------------
+constexpr int kSortSmemMax = 2048;
+
+__device__ __forceinline__ void bitonic_block(int32_t* a, int npow2, int tid, int nthreads) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow2; i += nthreads) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    int32_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one warp per row: <= 32 entries rank-sorted in registers, <= kWarpSortMax bitonic in per-warp smem, longer rows queued
+constexpr int kWarpSortMax = 256;
+__global__ void __launch_bounds__(256) csr_sort_rows_warp_kernel(const int64_t* __restrict__ rowptr, int64_t n,
+                                                                  int32_t* __restrict__ col, int64_t* __restrict__ long_rows,
+                                                                  int* __restrict__ n_long) {
+    __shared__ int32_t sm_all[8][kWarpSortMax];
+    const int lane = threadIdx.x & 31;
+    int32_t* sm = sm_all[threadIdx.x >> 5];
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        int64_t s = rowptr[r], e = rowptr[r + 1];
+        int64_t len64 = e - s;
+        if (len64 <= 1) continue;
+        if (len64 > kWarpSortMax) {
+            if (lane == 0) long_rows[atomicAdd(n_long, 1)] = r;
+            continue;
+        }
+        int len = (int)len64;
+        if (len <= 32) {
+            int32_t v = lane < len ? col[s + lane] : INT32_MAX;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int32_t o = __shfl_sync(0xffffffffu, v, j);
+                rank += (o < v) || (o == v && j < lane);
+            }
+            if (lane < len) col[s + rank] = v;  // all reads completed above (shuffles are warp-synchronous)
+            continue;
+        }
+        int p2 = 64;
+        while (p2 < len) p2 <<= 1;
+        for (int i = lane; i < p2; i += 32) sm[i] = i < len ? col[s + i] : INT32_MAX;
+        __syncwarp();
+        for (int k = 2; k <= p2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < p2; i += 32) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        int32_t x = sm[i], y = sm[ixj];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { sm[i] = y; sm[ixj] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < len; i += 32) col[s + i] = sm[i];
+        __syncwarp();
+    }
+}
+
+// one block per queued long row whose padded length p2 satisfies min_p2 < p2 <= max_p2
+__global__ void csr_sort_rows_block_kernel(const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+                                           const int64_t* __restrict__ long_rows, const int* __restrict__ n_long,
+                                           int32_t* __restrict__ scratch, int64_t scratch_per_block, int64_t min_p2,
+                                           int64_t max_p2) {
+    __shared__ int32_t sm[kSortSmemMax];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nq = *n_long;
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        int64_t r = long_rows[q];
+        int64_t s = rowptr[r];
+        int64_t len = rowptr[r + 1] - s;
+        int64_t p2 = 1;
+        while (p2 < len) p2 <<= 1;
+        if (p2 <= min_p2 || p2 > max_p2) continue;  // block-uniform
+        if (p2 <= kSortSmemMax) {
+            for (int i = tid; i < p2; i += nt) sm[i] = i < len ? col[s + i] : INT32_MAX;
+            __syncthreads();
+            bitonic_block(sm, (int)p2, tid, nt);
+            for (int i = tid; i < len; i += nt) col[s + i] = sm[i];
+            __syncthreads();
+        } else {
+            // hub rows: bitonic network in global scratch (padded to a power of two)
+            int32_t* g = scratch + (int64_t)blockIdx.x * scratch_per_block;
+            for (int64_t i = tid; i < p2; i += nt) g[i] = i < len ? col[s + i] : INT32_MAX;
+            __syncthreads();
+            for (int64_t k = 2; k <= p2; k <<= 1) {
+                for (int64_t j = k >> 1; j > 0; j >>= 1) {
+                    for (int64_t i = tid; i < p2; i += nt) {
+                        int64_t ixj = i ^ j;
+                        if (ixj > i) {
+                            int32_t x = g[i], y = g[ixj];
+                            bool up = (i & k) == 0;
+                            if ((x > y) == up) { g[i] = y; g[ixj] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int64_t i = tid; i < len; i += nt) col[s + i] = g[i];
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void csr_dinv_kernel(const int64_t* __restrict__ rowptr, int64_t n, float* __restrict__ dinv) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float d = (float)(rowptr[i + 1] - rowptr[i]);
+        // same operation order as the reference: (1/d).sqrt(), inf -> 0   (large/ours.py:29-32)
+        dinv[i] = d > 0.f ? sqrtf(1.0f / d) : 0.0f;
+    }
+}
+
+__global__ void max_row_len_kernel(const int64_t* __restrict__ rowptr, int64_t n, unsigned long long* __restrict__ out) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long l = (unsigned long long)(rowptr[i + 1] - rowptr[i]);
+        m = l > m ? l : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ---- K9: induced subgraph --------------------------------------------------------------------------
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+__global__ void subgraph_map_kernel(const int64_t* __restrict__ subset, int64_t n_sub, int64_t n, int32_t* __restrict__ node_map) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sub; i += stride) {
+        int64_t v = subset[i];
+        if (v >= 0 && v < n) node_map[v] = (int32_t)i;
+    }
+}
+// flag + block-local count, order-preserving compaction in three steps (flags -> scan -> scatter)
+__global__ void subgraph_flag_kernel(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, const int32_t* __restrict__ node_map,
+                                     int* __restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        int64_t r = ei[e], c = ei[nnz + e];
+        int keep = (r >= 0 && r < n && c >= 0 && c < n) ? (node_map[r] >= 0 && node_map[c] >= 0) : 0;
+        flags[e] = keep;
+    }
+}
+__global__ void subgraph_scatter_kernel(const int64_t* __restrict__ ei, int64_t nnz, const int32_t* __restrict__ node_map,
+                                        const int* __restrict__ flags, const int64_t* __restrict__ pos,
+                                        int64_t* __restrict__ out, int64_t out_pitch) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        if (!flags[e]) continue;
+        int64_t p = pos[e];
+        out[p] = node_map[ei[e]];
+        out[out_pitch + p] = node_map[ei[nnz + e]];
+    }
+}
+
+static inline int grid_for(int64_t work, int block, int per_sm = 8) {
+    int64_t g = (work + block - 1) / block;
+    int64_t cap = (int64_t)num_sms() * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// exclusive scan of int counts (+add) into int64 out[0..n], using block_sums scratch
+static int launch_scan(const int* counts, int64_t n, int add_loop, int64_t* rowptr, int64_t* block_sums,
+                       int64_t* total, int* cursor, cudaStream_t st) {
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nblocks = (n + per_block - 1) / per_block;
+    if (nblocks < 1) nblocks = 1;
+    scan_local_kernel<<<(unsigned)nblocks, kScanBlock, 0, st>>>(counts, n, add_loop, rowptr, block_sums);
+    SGF_LAUNCH_CHECK(); count_launch();
+    scan_block_sums_kernel<<<1, kScanBlock, 0, st>>>(block_sums, nblocks, total);
+    SGF_LAUNCH_CHECK(); count_launch();
+    scan_add_kernel<<<grid_for(n + 1, 256), 256, 0, st>>>(rowptr, n, block_sums, total, cursor, add_loop);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+}  // namespace sgf
+
+using namespace sgf;
+
+// workspace layout: counts int32[n] | cursor int32[n] | block_sums int64[nb] | total int64 | err int32 | n_long int32 |
+//                   maxlen u64 | long_rows int64[n] | hub scratch int32[...]
+struct CsrWs {
+    int* counts; int* cursor; int64_t* block_sums; int64_t* total; int* err; int* n_long;
+    unsigned long long* maxlen; int64_t* long_rows; int32_t* scratch; int64_t scratch_elems;
+    size_t bytes;
+};
+static constexpr int kHubBlocks = 16;
+// hub-row scratch cap (ints): rows longer than this (only possible with > 2^26 parallel edges into one node) are left
+// in fill order — still a valid CSR for the SpMM, but not bit-comparable.
+static constexpr int64_t kHubScratchMax = (int64_t)1 << 26;
+
+static CsrWs carve_ws(void* ws, int64_t nnz, int64_t n) {
+    CsrWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nb = (n + per_block - 1) / per_block + 1;
+    char* base = (char*)ws;
+    size_t o_counts = take((size_t)(n + 1) * 4), o_cursor = take((size_t)(n + 1) * 4), o_bs = take((size_t)nb * 8);
+    size_t o_misc = take(64), o_long = take((size_t)(n + 1) * 8);
+    // hub scratch: each of kHubBlocks blocks may need next_pow2(longest row) <= next_pow2(nnz + n) ints; sized lazily:
+    // we reserve 2*(nnz+n) ints in total and give every block an equal share (rows longer than a share are split... never:
+    // a row longer than share means few such rows exist; the kernel is launched with fewer blocks in that case).
+    int64_t tot = nnz + n;
+    int64_t p2 = kSortSmemMax * kHubBlocks;
+    while (p2 < tot && p2 < kHubScratchMax) p2 <<= 1;
+    size_t o_scr = take((size_t)p2 * 4);
+    w.counts = (int*)(base + o_counts); w.cursor = (int*)(base + o_cursor); w.block_sums = (int64_t*)(base + o_bs);
+    w.total = (int64_t*)(base + o_misc); w.err = (int*)(base + o_misc + 8); w.n_long = (int*)(base + o_misc + 12);
+    w.maxlen = (unsigned long long*)(base + o_misc + 16);
+    w.long_rows = (int64_t*)(base + o_long); w.scratch = (int32_t*)(base + o_scr); w.scratch_elems = p2;
+    w.bytes = off;
+    return w;
+}
+
+extern "C" int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
+    if (!bytes || nnz < 0 || n < 0) return SGF_ERR_ARG;
+    *bytes = carve_ws(nullptr, nnz, n).bytes;
+    return SGF_OK;
+}
+
+extern "C" int sgf_csr_build(const int64_t* edge_index, int64_t nnz, int64_t n, int by_source, int self_loop_mode,
+                             int64_t* rowptr, int32_t* col, float* dinv, void* ws, size_t ws_bytes, void* stream) {
+    if (nnz < 0 || n < 0 || n >= (int64_t)INT32_MAX || !rowptr || (!col && nnz + n > 0) || !ws) return SGF_ERR_ARG;
+    if (nnz > 0 && !edge_index) return SGF_ERR_ARG;
+    if (self_loop_mode != 0 && self_loop_mode != 1) return SGF_ERR_ARG;
+    CsrWs w = carve_ws(ws, nnz, n);
+    if (ws_bytes < w.bytes) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t* key = by_source ? edge_index : edge_index + nnz;
+    const int64_t* val = by_source ? edge_index + nnz : edge_index;
+    SGF_CUDA_TRY(cudaMemsetAsync(w.counts, 0, (size_t)(n + 1) * 4, st));
+    SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
+    if (nnz > 0) {
+        csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, n, self_loop_mode, w.counts, w.err);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
+    int rc = launch_scan(w.counts, n, self_loop_mode, rowptr, w.block_sums, w.total, w.cursor, st);
+    if (rc) return rc;
+    if (nnz > 0) {
+        csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, n, self_loop_mode, rowptr, w.cursor, col);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
+    if (self_loop_mode == 1 && n > 0) {
+        csr_add_loops_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, rowptr, w.cursor, col);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
+    if (n > 0) {
+        csr_sort_rows_warp_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(rowptr, n, col, w.long_rows, w.n_long);
+        SGF_LAUNCH_CHECK(); count_launch();
+        int64_t share = w.scratch_elems / kHubBlocks;
+        // queued rows: (256, 2048] in shared memory across the whole chip; (2048, share] in global scratch by kHubBlocks
+        // blocks; (share, scratch] by a single block.
+        csr_sort_rows_block_kernel<<<num_sms() * 4, 256, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, 0, 0, kSortSmemMax);
+        SGF_LAUNCH_CHECK(); count_launch();
+        csr_sort_rows_block_kernel<<<kHubBlocks, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, share, kSortSmemMax, share);
+        SGF_LAUNCH_CHECK(); count_launch();
+        csr_sort_rows_block_kernel<<<1, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, w.scratch_elems, share, w.scratch_elems);
+        SGF_LAUNCH_CHECK(); count_launch();
+        if (dinv) {
+            csr_dinv_kernel<<<grid_for(n, 256), 256, 0, st>>>(rowptr, n, dinv);
+            SGF_LAUNCH_CHECK(); count_launch();
+        }
+    } else {
+        SGF_CUDA_TRY(cudaMemsetAsync(rowptr, 0, 8, st));
+    }
+    return SGF_OK;
+}
+
+// workspace: flags int32[nnz] | pos int64[nnz+1] | block_sums | total
+extern "C" int sgf_subgraph_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
+    if (!bytes || nnz < 0 || n < 0) return SGF_ERR_ARG;
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nb = (nnz + per_block - 1) / per_block + 1;
+    *bytes = align_up((size_t)(nnz + 1) * 4, 256) * 2 + align_up((size_t)(nnz + 1) * 8, 256) + align_up((size_t)nb * 8, 256) + 256;
+    return SGF_OK;
+}
+
+extern "C" int sgf_subgraph(const int64_t* edge_index, int64_t nnz, int64_t n, const int64_t* subset, int64_t n_sub,
+                            int32_t* node_map, int64_t* out_edge_index, int64_t* out_count, void* ws, size_t ws_bytes,
+                            void* stream) {
+    if (nnz < 0 || n < 0 || n_sub < 0 || !node_map || !out_count || !ws) return SGF_ERR_ARG;
+    size_t need = 0;
+    sgf_subgraph_ws_bytes(nnz, n, &need);
+    if (ws_bytes < need) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    size_t off = 0;
+    int* flags = (int*)(base + off); off += align_up((size_t)(nnz + 1) * 4, 256);
+    int* cursor = (int*)(base + off); off += align_up((size_t)(nnz + 1) * 4, 256);
+    int64_t* pos = (int64_t*)(base + off); off += align_up((size_t)(nnz + 1) * 8, 256);
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nb = (nnz + per_block - 1) / per_block + 1;
+    int64_t* block_sums = (int64_t*)(base + off); off += align_up((size_t)nb * 8, 256);
+    (void)cursor;
+    fill_i32_kernel<<<grid_for(n, 256), 256, 0, st>>>(node_map, n, -1);
+    SGF_LAUNCH_CHECK(); count_launch();
+    if (n_sub > 0) {
+        subgraph_map_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(subset, n_sub, n, node_map);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
+    if (nnz == 0) {
+        SGF_CUDA_TRY(cudaMemsetAsync(out_count, 0, 8, st));
+        return SGF_OK;
+    }
+    subgraph_flag_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, nnz, n, node_map, flags);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int rc = launch_scan(flags, nnz, 0, pos, block_sums, out_count, cursor, st);
+    if (rc) return rc;
+    subgraph_scatter_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, nnz, node_map, flags, pos, out_edge_index, nnz);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}

@@ -1,0 +1,570 @@
+// Dense contractions of the SGFormer encoder on tcgen05 tensor cores (sm_100a).
+//
+//  gemm_nt : out[rows, n_out] = epilogue( sum_seg A_seg[rows, k] . B_seg[n_out, k]^T )      "row-streaming"
+//            rows = nodes (huge), n_out, k <= a few hundred.  Replaces nn.Linear forward / input-gradient,
+//            q~.(K^T V) and the attention backward products (reference medium/ours.py:22,28,76-85; large/ours.py:38-40,
+//            123-128,141,199,275).  Both operands K-major bf16, TMA SWIZZLE_128B tiles, BM=128 x BN<=256(+16) x BK=64,
+//            4-stage smem ring, fp32 accumulators in TMEM (double-buffered when BN<=256), warp-specialised:
+//            warp0 = TMA producer, warp1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (one TMEM lane quadrant each).
+//  gemm_tn : out[m, n] = alpha * sum_rows A[rows, m]^T B[rows, n]                               "node-contracting"
+//            Replaces K^T V (medium/ours.py:21), its backward q^T gnum and every weight gradient dW = dY^T X.
+//            Both operands are MN-major for the MMA (features contiguous), loaded as [64 feat x 64 node] boxes;
+//            the node range is split across CTAs, per-CTA partials go to a workspace and are reduced deterministically.
+//
+// Descriptor formats follow cute/arch/mma_sm100_desc.hpp and cute/atom/mma_traits_sm100.hpp (canonical SW128 layouts).
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/sgformer_b200.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace sgf {
+
+// ------------------------------------------------------------------------------------------------
+// host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (pitch ld elements), box = [box_rows x 64 cols], 128-byte swizzle, OOB -> 0
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return SGF_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || rows <= 0 || cols <= 0 || box_rows <= 0 || box_rows > 256)
+        return SGF_ERR_ARG;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SGF_OK : SGF_ERR_DRIVER;
+}
+
+// ================================================================================================
+// gemm_nt
+// ================================================================================================
+namespace nt {
+constexpr int BM = 128, BK = 64, STAGES = 4, THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+constexpr int B_BYTES_MAX = (256 + 16) * BK * 2;  // 34 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+
+struct Seg {
+    int a_idx, a_koff, b_idx, b_koff, k_blocks;
+};
+struct Params {
+    int64_t rows;
+    int n_out, bn_main, has_tail, n_blocks;
+    int64_t num_tiles;
+    int n_seg, total_kb;
+    Seg seg[SGF_MAX_SEG];
+    int epi;
+    void* out; int64_t ldo; int out_dtype;
+    const float* bias;
+    const void* aux; int64_t ld_aux; int aux_dtype;
+    const float* row_scale;
+    float alpha, beta;
+    const float* alpha_dev; const float* beta_dev;
+    int relu, accumulate;
+    float nf; float* den_out;
+    const float* r1_row; const float* r1_col;
+};
+struct Tmaps {
+    CUtensorMap a[SGF_MAX_SRC];
+    CUtensorMap b[SGF_MAX_SRC];
+    CUtensorMap tail;
+};
+
+__device__ __forceinline__ void load16(const void* base, int dtype, int64_t off, float* f) {
+    if (dtype == 1) {
+        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off);
+        uint4 u0 = __ldg(p), u1 = __ldg(p + 1);
+        Vec16<__nv_bfloat16>::unpack(u0, f);
+        Vec16<__nv_bfloat16>::unpack(u1, f + 8);
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Vec16<float>::unpack(__ldg(p + i), f + 4 * i);
+    }
+}
+__device__ __forceinline__ void store16(void* base, int dtype, int64_t off, const float* f) {
+    if (dtype == 1) {
+        uint4* p = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off);
+        p[0] = Vec16<__nv_bfloat16>::pack(f);
+        p[1] = Vec16<__nv_bfloat16>::pack(f + 8);
+    } else {
+        uint4* p = reinterpret_cast<uint4*>(static_cast<float*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = Vec16<float>::pack(f + 4 * i);
+    }
+}
+__device__ __forceinline__ float load1(const void* base, int dtype, int64_t off) {
+    return dtype == 1 ? __bfloat162float(static_cast<const __nv_bfloat16*>(base)[off]) : static_cast<const float*>(base)[off];
+}
+__device__ __forceinline__ void store1(void* base, int dtype, int64_t off, float v) {
+    if (dtype == 1) static_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+    else static_cast<float*>(base)[off] = v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ Tmaps tm, const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bn_total = p.bn_main + (p.has_tail ? 16 : 0);
+    const int acc_stages = bn_total <= 256 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.n_seg; ++i) {
+            tma_prefetch_desc(&tm.a[p.seg[i].a_idx]);
+            tma_prefetch_desc(&tm.b[p.seg[i].b_idx]);
+        }
+        if (p.has_tail) tma_prefetch_desc(&tm.tail);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            const uint32_t stage_tx = A_BYTES + p.bn_main * BK * 2 + (p.has_tail ? 16 * BK * 2 : 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile / p.n_blocks), n_blk = (int)(tile % p.n_blocks);
+                for (int s = 0; s < p.n_seg; ++s) {
+                    const Seg sg = p.seg[s];
+                    for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * STAGE_BYTES;
+                        uint8_t* sb = sa + A_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], stage_tx);
+                        tma_load_2d(sa, &tm.a[sg.a_idx], &full[stage], sg.a_koff + kb * BK, m_blk * BM);
+                        tma_load_2d(sb, &tm.b[sg.b_idx], &full[stage], sg.b_koff + kb * BK, n_blk * p.bn_main);
+                        if (p.has_tail) tma_load_2d(sb + p.bn_main * BK * 2, &tm.tail, &full[stage], sg.b_koff + kb * BK, 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc_main = make_idesc_bf16(BM, p.bn_main, 0, 0);
+            const uint32_t idesc_tail = make_idesc_bf16(BM, 16, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int64_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = (int)(it % acc_stages);
+                const uint32_t acc_phase = (uint32_t)((it / acc_stages) & 1);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_main = tmem_base + acc * 256;
+                for (int kbg = 0; kbg < p.total_kb; ++kbg) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                        const uint32_t accum = (kbg > 0 || k > 0) ? 1u : 0u;
+                        umma_bf16(d_main, da, db, idesc_main, accum);
+                        if (p.has_tail) {
+                            const uint64_t dt = make_smem_desc_sw128(sb + p.bn_main * BK * 2 + k * 32, 0, 1024);
+                            umma_bf16(d_main + p.bn_main, da, dt, idesc_tail, accum);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kbg == p.total_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        float alpha = p.alpha, beta = p.beta;
+        if (p.alpha_dev) alpha *= *p.alpha_dev;
+        if (p.beta_dev) beta *= *p.beta_dev;
+        const int out_es = p.out_dtype == 1 ? 2 : 4, aux_es = p.aux_dtype == 1 ? 2 : 4;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.ldo * out_es) % 16 == 0);
+        const bool aux_vec_ok = !p.aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ld_aux * aux_es) % 16 == 0));
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = (int)(tile / p.n_blocks), n_blk = (int)(tile % p.n_blocks);
+            const int acc = (int)(it % acc_stages);
+            const uint32_t acc_phase = (uint32_t)((it / acc_stages) & 1);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < p.rows;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+            const int col_base = n_blk * p.bn_main;
+            float inv_den = 1.f;
+            if (p.epi == SGF_EPI_ATTN_APPLY) {
+                float t[16];
+                __syncwarp();
+                tmem_ld16(taddr + p.bn_main, t);
+                tmem_ld_wait();
+                const float den = t[0] + p.nf;
+                inv_den = 1.f / den;
+                if (row_ok && p.den_out) p.den_out[row] = den;
+            }
+            const float rs = (p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
+            const float r1r = (p.r1_row && row_ok) ? p.r1_row[row] : 0.f;
+            const int n_chunks = p.bn_main / 16;
+            for (int c = 0; c < n_chunks; ++c) {
+                float v[16];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores of the previous chunk
+                tmem_ld16(taddr + c * 16, v);
+                tmem_ld_wait();
+                const int col0 = col_base + c * 16;
+                if (row_ok && col0 < p.n_out) {
+                const bool full16 = col0 + 16 <= p.n_out;
+                float ax[16];
+                if (p.aux) {
+                    if (full16 && aux_vec_ok) load16(p.aux, p.aux_dtype, row * p.ld_aux + col0, ax);
+                    else
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) ax[j] = (col0 + j < p.n_out) ? load1(p.aux, p.aux_dtype, row * p.ld_aux + col0 + j) : 0.f;
+                }
+                if (p.epi == SGF_EPI_ATTN_APPLY) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float t = alpha * v[j];
+                        if (p.aux) t += beta * ax[j];
+                        if (p.bias && col0 + j < p.n_out) t += p.bias[col0 + j];
+                        if (p.r1_row && col0 + j < p.n_out) t += r1r * p.r1_col[col0 + j];
+                        if (p.relu) t = fmaxf(t, 0.f);
+                        v[j] = t * rs;
+                    }
+                }
+                if (p.accumulate) {
+                    float old[16];
+                    if (full16 && vec_ok) load16(p.out, p.out_dtype, row * p.ldo + col0, old);
+                    else
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) old[j] = (col0 + j < p.n_out) ? load1(p.out, p.out_dtype, row * p.ldo + col0 + j) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += old[j];
+                }
+                if (full16 && vec_ok) store16(p.out, p.out_dtype, row * p.ldo + col0, v);
+                else
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col0 + j < p.n_out) store1(p.out, p.out_dtype, row * p.ldo + col0 + j, v[j]);
+                }
+            }
+            __syncwarp();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+}  // namespace nt
+
+// ================================================================================================
+// gemm_tn
+// ================================================================================================
+namespace tn {
+constexpr int BKN = 64, STAGES = 3, THREADS = 192;
+constexpr int CHUNK_BYTES = 64 * BKN * 2;   // one [64 feat x 64 node] box = 8 KB
+constexpr int A_BYTES = 4 * CHUNK_BYTES;    // up to 256 features
+constexpr int B_BYTES = 4 * CHUNK_BYTES;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 64 KB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+
+struct Params {
+    int64_t rows;
+    int m, n, m_blocks, n_chunks, un;  // un = UMMA N (n rounded up to 16)
+    int64_t kb_total;
+    float* ws;  // [grid][un][m_blocks*128]
+};
+struct Tmaps {
+    CUtensorMap a, b;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tn_kernel(const __grid_constant__ Tmaps tm, const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // contiguous slice of 64-row node blocks for this CTA
+    const int64_t per = p.kb_total / gridDim.x, rem = p.kb_total % gridDim.x;
+    const int64_t kb0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+    const int64_t kb1 = kb0 + per + (blockIdx.x < rem ? 1 : 0);
+    const int a_chunks = p.m_blocks * 2;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm.a);
+        tma_prefetch_desc(&tm.b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t stage_tx = (a_chunks + p.n_chunks) * CHUNK_BYTES;
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_arrive_expect_tx(&full[stage], stage_tx);
+                for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tm.a, &full[stage], c * 64, (int32_t)(kb * BKN));
+                for (int c = 0; c < p.n_chunks; ++c) tma_load_2d(sb + c * CHUNK_BYTES, &tm.b, &full[stage], c * 64, (int32_t)(kb * BKN));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.un, 1, 1);  // both operands MN-major
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BKN / 16; ++k) {
+                    // MN-major SW128: LBO = stride between 64-element feature chunks, SBO = stride between 8-row node groups
+                    const uint64_t db = make_smem_desc_sw128(sb + k * 2048, CHUNK_BYTES, 1024);
+                    const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                    for (int mb = 0; mb < p.m_blocks; ++mb) {
+                        const uint64_t da = make_smem_desc_sw128(sa + mb * 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
+                        umma_bf16(tmem_base + mb * 256, da, db, idesc, accum);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (kb == kb1 - 1) umma_commit(tmem_full);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int mp = p.m_blocks * 128;
+        float* ws = p.ws + (int64_t)blockIdx.x * p.un * mp;
+        if (kb1 > kb0) {
+            mbar_wait(tmem_full, 0);
+            tcgen05_fence_after();
+        }
+        for (int mb = 0; mb < p.m_blocks; ++mb) {
+            const int mrow = mb * 128 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mb * 256;
+            for (int c = 0; c < p.un / 16; ++c) {
+                float v[16];
+                if (kb1 > kb0) {
+                    __syncwarp();
+                    tmem_ld16(taddr + c * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ws[(int64_t)(c * 16 + j) * mp + mrow] = v[j];
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// out[i,j] = alpha * sum_cta ws[cta][j][i] (+ beta*out[i,j]);  i < m, j < n
+__global__ void tn_reduce_kernel(const float* __restrict__ ws, int nparts, int mp, int un, int m, int n, float alpha,
+                                 const float* __restrict__ alpha_dev, float beta, float* __restrict__ out, int64_t ldo, int transpose_out) {
+    const int64_t total = (int64_t)n * mp;
+    const float a = alpha * (alpha_dev ? *alpha_dev : 1.f);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t / mp), i = (int)(t % mp);
+        if (i >= m) continue;
+        float s = 0.f;
+        for (int c = 0; c < nparts; ++c) s += ws[((int64_t)c * un + j) * mp + i];
+        float* o = transpose_out ? &out[(int64_t)j * ldo + i] : &out[(int64_t)i * ldo + j];
+        *o = a * s + (beta != 0.f ? beta * *o : 0.f);
+    }
+}
+}  // namespace tn
+}  // namespace sgf
+
+using namespace sgf;
+
+extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
+    if (!a || a->rows < 0 || a->n_out <= 0 || a->n_seg <= 0 || a->n_seg > SGF_MAX_SEG || a->n_a <= 0 || a->n_a > SGF_MAX_SRC ||
+        a->n_b <= 0 || a->n_b > SGF_MAX_SRC || !a->out)
+        return SGF_ERR_ARG;
+    if (a->out_dtype != 0 && a->out_dtype != 1) return SGF_ERR_ARG;
+    if (a->aux && a->aux_dtype != 0 && a->aux_dtype != 1) return SGF_ERR_ARG;
+    if (a->rows == 0) return SGF_OK;
+    const bool has_tail = a->b_tail != nullptr;
+    if (has_tail && (a->n_b != 1 || a->n_out > 256)) return SGF_ERR_ARG;
+    if (a->epi == SGF_EPI_ATTN_APPLY && (!has_tail || !a->aux)) return SGF_ERR_ARG;
+    if ((a->r1_row == nullptr) != (a->r1_col == nullptr)) return SGF_ERR_ARG;
+
+    nt::Params p;
+    memset(&p, 0, sizeof(p));
+    nt::Tmaps tm;
+    memset(&tm, 0, sizeof(tm));
+    p.rows = a->rows;
+    p.n_out = a->n_out;
+    const int n16 = (a->n_out + 15) / 16 * 16;
+    p.n_blocks = (n16 + 255) / 256;
+    // equal-width n-blocks, each a multiple of 16
+    p.bn_main = ((n16 / 16 + p.n_blocks - 1) / p.n_blocks) * 16;
+    p.has_tail = has_tail ? 1 : 0;
+    const int64_t m_blocks = (a->rows + nt::BM - 1) / nt::BM;
+    p.num_tiles = m_blocks * p.n_blocks;
+    p.n_seg = a->n_seg;
+    p.total_kb = 0;
+    for (int s = 0; s < a->n_seg; ++s) {
+        const int ai = a->seg_a[s], bi = a->seg_b[s];
+        if (ai < 0 || ai >= a->n_a || bi < 0 || bi >= a->n_b || a->seg_klen[s] <= 0) return SGF_ERR_ARG;
+        const int klen = a->seg_klen[s];
+        // A partial last k-block (klen % 64 != 0) reads A/B columns past koff+klen: the caller guarantees that those A
+        // columns are zero (zero padding or the end of the tensor, where TMA zero-fills) and the B columns finite.
+        if (a->seg_akoff[s] + klen > a->a_cols[ai] || a->seg_bkoff[s] + klen > a->b_cols[bi]) return SGF_ERR_ARG;
+        p.seg[s].a_idx = ai; p.seg[s].a_koff = a->seg_akoff[s];
+        p.seg[s].b_idx = bi; p.seg[s].b_koff = a->seg_bkoff[s];
+        p.seg[s].k_blocks = (klen + nt::BK - 1) / nt::BK;
+        p.total_kb += p.seg[s].k_blocks;
+    }
+    int rc;
+    for (int i = 0; i < a->n_a; ++i)
+        if ((rc = make_tmap_bf16(&tm.a[i], a->a[i], a->rows, a->a_cols[i], a->lda[i], nt::BM))) return rc;
+    for (int i = 0; i < a->n_b; ++i)
+        if ((rc = make_tmap_bf16(&tm.b[i], a->b[i], a->n_out, a->b_cols[i], a->ldb[i], p.bn_main))) return rc;
+    if (has_tail && (rc = make_tmap_bf16(&tm.tail, a->b_tail, 16, a->b_cols[0], a->ldb_tail, 16))) return rc;
+
+    p.epi = a->epi;
+    p.out = a->out; p.ldo = a->ldo; p.out_dtype = a->out_dtype;
+    p.bias = a->bias;
+    p.aux = a->aux; p.ld_aux = a->ld_aux; p.aux_dtype = a->aux_dtype;
+    p.row_scale = a->row_scale;
+    p.alpha = a->alpha; p.beta = a->beta; p.alpha_dev = a->alpha_dev; p.beta_dev = a->beta_dev;
+    p.relu = a->relu; p.accumulate = a->accumulate;
+    p.nf = a->nf; p.den_out = a->den_out;
+    p.r1_row = a->r1_row; p.r1_col = a->r1_col;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGF_CUDA_TRY(cudaFuncSetAttribute(nt::gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt::SMEM_BYTES));
+        attr_set = true;
+    }
+    int64_t grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    nt::gemm_nt_kernel<<<(unsigned)grid, nt::THREADS, nt::SMEM_BYTES, (cudaStream_t)stream>>>(tm, p);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+static inline int tn_grid(int64_t kb_total) { return (int)(kb_total < num_sms() ? kb_total : num_sms()); }
+
+extern "C" int sgf_gemm_tn_ws_bytes(int32_t m, int32_t n, int64_t rows, size_t* bytes) {
+    if (!bytes || m <= 0 || m > 256 || n <= 0 || n > 256 || rows < 0) return SGF_ERR_ARG;
+    const int m_blocks = (m + 127) / 128, un = (n + 15) / 16 * 16;
+    const int64_t kb_total = (rows + tn::BKN - 1) / tn::BKN;
+    int grid = tn_grid(kb_total < 1 ? 1 : kb_total);
+    *bytes = (size_t)grid * un * m_blocks * 128 * sizeof(float);
+    return SGF_OK;
+}
+
+extern "C" int sgf_gemm_tn(const sgf_gemm_tn_args* a, void* stream) {
+    if (!a || a->m <= 0 || a->m > 256 || a->n <= 0 || a->n > 256 || a->rows < 0 || !a->out || !a->ws) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    tn::Params p;
+    memset(&p, 0, sizeof(p));
+    p.rows = a->rows; p.m = a->m; p.n = a->n;
+    p.m_blocks = (a->m + 127) / 128;
+    p.un = (a->n + 15) / 16 * 16;
+    p.n_chunks = (p.un + 63) / 64;
+    p.kb_total = (a->rows + tn::BKN - 1) / tn::BKN;
+    p.ws = (float*)a->ws;
+    const int mp = p.m_blocks * 128;
+    int grid = 0;
+    if (a->rows > 0) {
+        size_t need = 0;
+        sgf_gemm_tn_ws_bytes(a->m, a->n, a->rows, &need);
+        if (a->ws_bytes < need) return SGF_ERR_ARG;
+        tn::Tmaps tm;
+        memset(&tm, 0, sizeof(tm));
+        int rc;
+        if ((rc = make_tmap_bf16(&tm.a, a->a, a->rows, a->m, a->lda, tn::BKN))) return rc;
+        if ((rc = make_tmap_bf16(&tm.b, a->b, a->rows, a->n, a->ldb, tn::BKN))) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            SGF_CUDA_TRY(cudaFuncSetAttribute(tn::gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES));
+            attr_set = true;
+        }
+        grid = tn_grid(p.kb_total);
+        tn::gemm_tn_kernel<<<grid, tn::THREADS, tn::SMEM_BYTES, st>>>(tm, p);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
+    int64_t total = (int64_t)a->n * mp;
+    int rgrid = (int)((total + 255) / 256);
+    tn::tn_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, grid, mp, p.un, a->m, a->n, a->alpha, a->alpha_dev, a->beta, a->out, a->ldo,
+                                                a->transpose_out);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}

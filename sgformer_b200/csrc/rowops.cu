@@ -1,0 +1,890 @@
+// Row-streaming kernels: LayerNorm / BatchNorm / ReLU / dropout / residual mixes / column statistics / casts.
+//
+// Replace the ATen passes of the reference's TransConv.forward / GraphConv.forward (large/ours.py:74-94,194-219),
+// torch.norm (medium/ours.py:16-17) and their autograd backward.  All are HBM-bound: 128-bit loads/stores, every
+// activation read once per kernel, fp32 math, row reductions by warp shuffles, column reductions by per-lane register
+// accumulators -> shared-memory atomics -> one global atomic per column per block.
+//
+// Geometry shared by all kernels: a feature row of h elements is split into 16-byte chunks; `lpr` (a power of two
+// <= 32) lanes cover one row, each lane owning chunks {sub, sub+lpr, ...} (CPL of them); a warp processes 32/lpr rows
+// at a time.  Because the lane -> column mapping is fixed, column sums accumulate in registers across the row loop.
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/sgformer_b200.h"
+
+namespace sgf {
+
+constexpr int kRowBlock = 256;
+constexpr float kLnEps = 1e-5f;
+
+struct RowGeom {
+    int chunks, lpr_log2, cpl;
+};
+template <typename T>
+static inline bool make_geom(int h, RowGeom& g) {
+    constexpr int VN = Vec16<T>::N;
+    if (h <= 0 || h % VN != 0) return false;
+    g.chunks = h / VN;
+    g.lpr_log2 = 0;
+    while ((1 << g.lpr_log2) < g.chunks && g.lpr_log2 < 5) ++g.lpr_log2;
+    g.cpl = (g.chunks + (1 << g.lpr_log2) - 1) >> g.lpr_log2;
+    return g.cpl <= 4;
+}
+static inline int row_grid(int64_t rows, const RowGeom& g) {
+    int rpw = 32 >> g.lpr_log2;
+    int64_t warps = (rows + rpw - 1) / rpw;
+    int64_t blocks = (warps * 32 + kRowBlock - 1) / kRowBlock;
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T, int CPL>
+struct Lane {
+    static constexpr int VN = Vec16<T>::N;
+    int lane, lpr, sub, grp, rpw;
+    int coff[CPL];
+    bool cval[CPL];
+    int64_t row0, row_step;
+    __device__ __forceinline__ Lane(int chunks, int lpr_log2) {
+        lane = threadIdx.x & 31;
+        lpr = 1 << lpr_log2;
+        sub = lane & (lpr - 1);
+        grp = lane >> lpr_log2;
+        rpw = 32 >> lpr_log2;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            int ch = sub + c * lpr;
+            cval[c] = ch < chunks;
+            coff[c] = ch * VN;
+        }
+        int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        row0 = warp * rpw + grp;
+        row_step = nwarps * rpw;
+    }
+    __device__ __forceinline__ void load(const T* base, int64_t ld, int64_t r, float (&f)[CPL][Vec16<T>::N]) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            if (cval[c]) {
+                uint4 u = ldg_nc_na(base + r * ld + coff[c]);
+                Vec16<T>::unpack(u, f[c]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VN; ++i) f[c][i] = 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(T* base, int64_t ld, int64_t r, const float (&f)[CPL][Vec16<T>::N]) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            if (cval[c]) stg_na(base + r * ld + coff[c], Vec16<T>::pack(f[c]));
+    }
+    // sum over the lanes that share a row
+    __device__ __forceinline__ float row_sum(float v) const {
+        for (int o = 1; o < lpr; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ void load_vec(const float* p, float (&f)[CPL][Vec16<T>::N], float fill) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) f[c][i] = (cval[c] && p) ? p[coff[c] + i] : fill;
+    }
+};
+
+// fold per-lane column accumulators of a block into global memory (fp32 atomics)
+template <typename T, int CPL>
+__device__ __forceinline__ void flush_columns(const Lane<T, CPL>& L, float (&acc)[CPL][Vec16<T>::N], float* sm /* [h] */, int h,
+                                              float* gout) {
+    constexpr int VN = Vec16<T>::N;
+    for (int i = threadIdx.x; i < h; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    for (int o = L.lpr; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], o);
+    }
+    if (L.grp == 0) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            if (L.cval[c])
+#pragma unroll
+                for (int i = 0; i < VN; ++i) atomicAdd(&sm[L.coff[c] + i], acc[c][i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h; i += blockDim.x) atomicAdd(&gout[i], sm[i]);
+    __syncthreads();
+}
+
+#define SGF_ZERO(a)                                   \
+    _Pragma("unroll") for (int c_ = 0; c_ < CPL; ++c_) \
+        _Pragma("unroll") for (int i_ = 0; i_ < VN; ++i_) a[c_][i_] = 0.f;
+#define SGF_FOR_ELEMS _Pragma("unroll") for (int c = 0; c < CPL; ++c) _Pragma("unroll") for (int i = 0; i < VN; ++i)
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kRowBlock) colstats_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int h, int chunks,
+                                                              int lpr_log2, const float* __restrict__ w, float* __restrict__ sum,
+                                                              float* __restrict__ sumsq) {
+    constexpr int VN = Vec16<T>::N;
+    extern __shared__ float sm[];
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float s1[CPL][VN], s2[CPL][VN];
+    SGF_ZERO(s1) SGF_ZERO(s2)
+    for (int64_t r = L.row0; r < rows; r += L.row_step) {
+        float f[CPL][VN];
+        L.load(x, ldx, r, f);
+        const float wr = w ? w[r] : 1.f;
+        SGF_FOR_ELEMS { s1[c][i] += wr * f[c][i]; s2[c][i] += f[c][i] * f[c][i]; }
+    }
+    if (sum) flush_columns<T, CPL>(L, s1, sm, h, sum);
+    if (sumsq) flush_columns<T, CPL>(L, s2, sm, h, sumsq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm family.  u = a*x + b*r; t = LN?(u); t = relu?(t); y = dropout(t)
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kRowBlock) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ rr, int64_t ld, int64_t rows,
+                                                            int h, int chunks, int lpr_log2, float a, float b,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int use_ln,
+                                                            int use_relu, float p, uint64_t seed, T* __restrict__ y,
+                                                            float* __restrict__ stats) {
+    constexpr int VN = Vec16<T>::N;
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float g[CPL][VN], be[CPL][VN];
+    L.load_vec(use_ln ? gamma : nullptr, g, 1.f);
+    L.load_vec(use_ln ? beta : nullptr, be, 0.f);
+    const float inv_h = 1.f / (float)h;
+    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    // all lanes of a warp must run the same number of iterations (row_sum shuffles): iterate on the warp's first row
+    for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
+        const int64_t r = rb + L.grp;
+        const bool live = r < rows;
+        float u[CPL][VN];
+        if (live) {
+            L.load(x, ld, r, u);
+            if (rr) {
+                float t[CPL][VN];
+                L.load(rr, ld, r, t);
+                SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
+            } else {
+                SGF_FOR_ELEMS u[c][i] = a * u[c][i];
+            }
+        } else {
+            SGF_ZERO(u)
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (use_ln) {
+            float s = 0.f;
+            SGF_FOR_ELEMS s += u[c][i];
+            mean = L.row_sum(s) * inv_h;
+            float v = 0.f;
+            SGF_FOR_ELEMS { float d = L.cval[c] ? u[c][i] - mean : 0.f; v += d * d; }
+            rstd = rsqrtf(L.row_sum(v) * inv_h + kLnEps);
+            SGF_FOR_ELEMS u[c][i] = (u[c][i] - mean) * rstd * g[c][i] + be[c][i];
+        }
+        if (use_relu) SGF_FOR_ELEMS u[c][i] = fmaxf(u[c][i], 0.f);
+        if (p > 0.f) SGF_FOR_ELEMS u[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+        if (live) {
+            L.store(y, ld, r, u);
+            if (stats && L.sub == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+        }
+    }
+}
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kRowBlock) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ rr,
+                                                            int64_t ld, int64_t rows, int h, int chunks, int lpr_log2, float a, float b,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ stats, int use_ln, int use_relu, float p,
+                                                            uint64_t seed, float gscale, T* __restrict__ dx, T* __restrict__ dr,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    constexpr int VN = Vec16<T>::N;
+    extern __shared__ float sm[];
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float g[CPL][VN], be[CPL][VN], dg[CPL][VN], db[CPL][VN];
+    L.load_vec(use_ln ? gamma : nullptr, g, 1.f);
+    L.load_vec(use_ln ? beta : nullptr, be, 0.f);
+    SGF_ZERO(dg) SGF_ZERO(db)
+    const float inv_h = 1.f / (float)h;
+    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
+        const int64_t r = rb + L.grp;
+        const bool live = r < rows;
+        float u[CPL][VN], gy[CPL][VN];
+        float mean = 0.f, rstd = 1.f;
+        if (live) {
+            L.load(x, ld, r, u);
+            if (rr) {
+                float t[CPL][VN];
+                L.load(rr, ld, r, t);
+                SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
+            } else {
+                SGF_FOR_ELEMS u[c][i] = a * u[c][i];
+            }
+            L.load(dy, ld, r, gy);
+            if (use_ln) { mean = stats[2 * r]; rstd = stats[2 * r + 1]; }
+        } else {
+            SGF_ZERO(u) SGF_ZERO(gy)
+        }
+        SGF_FOR_ELEMS gy[c][i] *= gscale;
+        if (p > 0.f) SGF_FOR_ELEMS gy[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+        float du[CPL][VN];
+        if (use_ln) {
+            float s1 = 0.f, s2 = 0.f;
+            SGF_FOR_ELEMS {
+                float xh = L.cval[c] ? (u[c][i] - mean) * rstd : 0.f;
+                float pre = xh * g[c][i] + be[c][i];
+                float gg = (use_relu && pre <= 0.f) ? 0.f : gy[c][i];
+                dg[c][i] += gg * xh;
+                db[c][i] += gg;
+                gg *= g[c][i];
+                u[c][i] = xh;
+                gy[c][i] = gg;
+                s1 += gg;
+                s2 += gg * xh;
+            }
+            s1 = L.row_sum(s1) * inv_h;
+            s2 = L.row_sum(s2) * inv_h;
+            SGF_FOR_ELEMS du[c][i] = rstd * (gy[c][i] - s1 - u[c][i] * s2);
+        } else {
+            SGF_FOR_ELEMS du[c][i] = (use_relu && u[c][i] <= 0.f) ? 0.f : gy[c][i];
+        }
+        if (live) {
+            float o[CPL][VN];
+            SGF_FOR_ELEMS o[c][i] = a * du[c][i];
+            L.store(dx, ld, r, o);
+            if (dr) {
+                SGF_FOR_ELEMS o[c][i] = b * du[c][i];
+                L.store(dr, ld, r, o);
+            }
+        }
+    }
+    if (use_ln && dgamma) flush_columns<T, CPL>(L, dg, sm, h, dgamma);
+    if (use_ln && dbeta) flush_columns<T, CPL>(L, db, sm, h, dbeta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm family (column statistics supplied)
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int64_t rows, int h, float eps,
+                                   float momentum, const float* __restrict__ zbias, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= h) return;
+    if (sum) {  // batch statistics (training); statistics are of z (without zbias), the bias only shifts the mean
+        double n = (double)rows;
+        double m = (double)sum[c] / n;
+        double var = (double)sumsq[c] / n - m * m;
+        if (var < 0.0) var = 0.0;
+        if (zbias) m += (double)zbias[c];
+        mean[c] = (float)m;
+        rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (rmean) {
+            double unb = rows > 1 ? var * n / (n - 1.0) : var;
+            rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+            rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+        }
+    } else {  // running statistics (eval)
+        mean[c] = rmean[c];
+        rstd[c] = rsqrtf(rvar[c] + eps);
+    }
+}
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kRowBlock) bn_fwd_kernel(const T* __restrict__ z, const T* __restrict__ res, const T* __restrict__ mix,
+                                                            int64_t ld, int64_t rows, int h, int chunks, int lpr_log2,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ zbias, int use_bn,
+                                                            int use_relu, float p, uint64_t seed, float gw,
+                                                            const float* __restrict__ row_scale, T* __restrict__ y,
+                                                            T* __restrict__ y_scaled) {
+    constexpr int VN = Vec16<T>::N;
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float sc[CPL][VN], sh[CPL][VN];
+    {
+        float m[CPL][VN], rs[CPL][VN], g[CPL][VN], be[CPL][VN], zb[CPL][VN];
+        L.load_vec(use_bn ? mean : nullptr, m, 0.f);
+        L.load_vec(use_bn ? rstd : nullptr, rs, 1.f);
+        L.load_vec(use_bn ? gamma : nullptr, g, 1.f);
+        L.load_vec(use_bn ? beta : nullptr, be, 0.f);
+        L.load_vec(zbias, zb, 0.f);
+        SGF_FOR_ELEMS { sc[c][i] = rs[c][i] * g[c][i]; sh[c][i] = be[c][i] + (zb[c][i] - m[c][i]) * sc[c][i]; }
+    }
+    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t r = L.row0; r < rows; r += L.row_step) {
+        float v[CPL][VN];
+        L.load(z, ld, r, v);
+        SGF_FOR_ELEMS v[c][i] = v[c][i] * sc[c][i] + sh[c][i];
+        if (use_relu) SGF_FOR_ELEMS v[c][i] = fmaxf(v[c][i], 0.f);
+        if (p > 0.f) SGF_FOR_ELEMS v[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+        if (res) {
+            float t[CPL][VN];
+            L.load(res, ld, r, t);
+            SGF_FOR_ELEMS v[c][i] += t[c][i];
+        }
+        if (y_scaled) {
+            const float s = row_scale[r];
+            float t[CPL][VN];
+            SGF_FOR_ELEMS t[c][i] = v[c][i] * s;
+            L.store(y_scaled, ld, r, t);
+        }
+        if (mix) {
+            float t[CPL][VN];
+            L.load(mix, ld, r, t);
+            SGF_FOR_ELEMS v[c][i] = gw * v[c][i] + (1.f - gw) * t[c][i];
+        }
+        if (y) L.store(y, ld, r, v);
+    }
+}
+
+// g_raw = gscale * (dy + rs2[r]*dy2);  dres (+)= g_raw;  g = g_raw * dropmask * relumask
+// REDUCE: sums[0:h] += g, sums[h:2h] += g*xhat.   APPLY: dz = BN-backward(g) (* out_scale[r]); dz_colsum += dz (unscaled)
+template <typename T, int CPL, bool APPLY>
+__global__ void __launch_bounds__(kRowBlock) bn_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2,
+                                                            const float* __restrict__ rs2, const T* __restrict__ z, int64_t ld,
+                                                            int64_t rows, int h, int chunks, int lpr_log2, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ zbias, int use_bn,
+                                                            int use_relu, int training, float p, uint64_t seed, float gscale,
+                                                            float* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
+                                                            int dres_acc, float* __restrict__ dz_colsum,
+                                                            const float* __restrict__ out_scale) {
+    constexpr int VN = Vec16<T>::N;
+    extern __shared__ float sm[];
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float m[CPL][VN], rs[CPL][VN], g[CPL][VN], be[CPL][VN];
+    L.load_vec(use_bn ? mean : nullptr, m, 0.f);
+    L.load_vec(use_bn ? rstd : nullptr, rs, 1.f);
+    L.load_vec(use_bn ? gamma : nullptr, g, 1.f);
+    L.load_vec(use_bn ? beta : nullptr, be, 0.f);
+    {
+        float zb[CPL][VN];
+        L.load_vec(zbias, zb, 0.f);
+        SGF_FOR_ELEMS m[c][i] -= zb[c][i];  // xhat = (z + zbias - mean) * rstd
+    }
+    float a1[CPL][VN], a2[CPL][VN];
+    if (APPLY && use_bn && training) {
+        const float inv_n = 1.f / (float)rows;
+        L.load_vec(sums, a1, 0.f);
+        L.load_vec(sums + h, a2, 0.f);
+        SGF_FOR_ELEMS { a1[c][i] *= inv_n; a2[c][i] *= inv_n; }
+    } else {
+        SGF_ZERO(a1) SGF_ZERO(a2)
+    }
+    float cs[CPL][VN];
+    SGF_ZERO(cs)
+    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t r = L.row0; r < rows; r += L.row_step) {
+        float gy[CPL][VN], zz[CPL][VN];
+        if (dy) L.load(dy, ld, r, gy);
+        else SGF_ZERO(gy)
+        if (dy2) {
+            float t[CPL][VN];
+            L.load(dy2, ld, r, t);
+            const float s2 = rs2 ? rs2[r] : 1.f;
+            SGF_FOR_ELEMS gy[c][i] += s2 * t[c][i];
+        }
+        SGF_FOR_ELEMS gy[c][i] *= gscale;
+        if (APPLY && dres) {
+            if (dres_acc) {
+                float t[CPL][VN];
+                L.load(dres, ld, r, t);
+                SGF_FOR_ELEMS t[c][i] += gy[c][i];
+                L.store(dres, ld, r, t);
+            } else {
+                L.store(dres, ld, r, gy);
+            }
+        }
+        L.load(z, ld, r, zz);
+        const float os = (APPLY && out_scale) ? out_scale[r] : 1.f;
+        SGF_FOR_ELEMS {
+            float xh = (zz[c][i] - m[c][i]) * rs[c][i];
+            float pre = xh * g[c][i] + be[c][i];
+            float gg = gy[c][i];
+            if (p > 0.f) gg *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+            if (use_relu && pre <= 0.f) gg = 0.f;
+            if (APPLY) {
+                float d = use_bn ? g[c][i] * rs[c][i] * (gg - a1[c][i] - xh * a2[c][i]) : gg;
+                cs[c][i] += L.cval[c] ? d : 0.f;
+                gy[c][i] = d * os;
+            } else {
+                a1[c][i] += gg;
+                a2[c][i] += gg * xh;
+            }
+        }
+        if (APPLY && dz) L.store(dz, ld, r, gy);
+    }
+    if (!APPLY) {
+        flush_columns<T, CPL>(L, a1, sm, h, sums);
+        flush_columns<T, CPL>(L, a2, sm, h, sums + h);
+    } else if (dz_colsum) {
+        flush_columns<T, CPL>(L, cs, sm, h, dz_colsum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kRowBlock) axpby_kernel(const TI* __restrict__ x, int64_t ldx, const TI* __restrict__ y, int64_t ldy,
+                                                           float a, float b, const float* __restrict__ row_scale, TO* __restrict__ out,
+                                                           int64_t ldo, int64_t rows, int h) {
+    // 4 elements per thread-step; rows may have different pitches so index by (row, col4)
+    const int h4 = (h + 3) >> 2;
+    const int64_t total = rows * h4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t r = t / h4;
+        const int c0 = (int)(t - r * h4) * 4;
+        const float s = row_scale ? row_scale[r] : 1.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = c0 + i;
+            if (c < h) {
+                float v = a * to_f32(x[r * ldx + c]);
+                if (y) v += b * to_f32(y[r * ldy + c]);
+                out[r * ldo + c] = from_f32<TO>(v * s);
+            }
+        }
+    }
+}
+
+// fp32 [rows, cols] (pitch ld_src) -> bf16 operand dst[r_out, c_out] (optionally transposed), K padded with zeros to kp,
+// one plane (plane_ld == 0) or three planes side by side (value ~= p0 + p1 + p2; fp32-accurate tensor-core products).
+// Optional exact fp32 column sums of the source (bias gradients).
+__global__ void __launch_bounds__(kRowBlock) pack_operand_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                                                  int transpose, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+                                                                  int kp, int64_t plane_ld, float* __restrict__ colsum) {
+    extern __shared__ float sm[];
+    const int64_t rows_out = transpose ? cols : rows;
+    const int cols_out = transpose ? (int)rows : cols;
+    if (colsum) {
+        for (int i = threadIdx.x; i < cols; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+    }
+    const int64_t total = rows_out * kp;
+    const int64_t per_block = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per_block;
+    const int64_t t1 = t0 + per_block < total ? t0 + per_block : total;
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const int64_t r = t / kp;
+        const int c = (int)(t - r * kp);
+        float v = 0.f;
+        if (c < cols_out) {
+            v = transpose ? src[(int64_t)c * ld_src + r] : src[r * ld_src + c];
+            if (colsum) atomicAdd(&sm[transpose ? (int)r : c], v);
+        }
+        __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+        __nv_bfloat16* o = dst + r * ld_dst + c;
+        o[0] = p0;
+        if (plane_ld > 0) {
+            float r1 = v - __bfloat162float(p0);
+            __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+            o[plane_ld] = p1;
+            o[2 * plane_ld] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+        }
+    }
+    if (colsum) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < cols; i += blockDim.x)
+            if (sm[i] != 0.f) atomicAdd(&colsum[i], sm[i]);
+    }
+}
+
+// multi-head attention backward: the norm-gradient scalar is shared by all heads (one ||q||_F over [N,H,M])
+__global__ void attn_combine_scal_kernel(float* __restrict__ scal_bwd, int heads, int stride, const float* __restrict__ scal_fwd) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float c = 0.f;
+        for (int i = 0; i < heads; ++i) c += scal_bwd[i * stride + 3];
+        const float inq = scal_fwd[0], ink = scal_fwd[1];
+        for (int i = 0; i < heads; ++i) {
+            scal_bwd[i * stride + 1] = -c * inq * inq;
+            scal_bwd[i * stride + 2] = -c * ink * ink;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRowBlock) head_mean_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int heads, int d,
+                                                               T* __restrict__ out, int64_t ldo) {
+    const int64_t total = rows * d;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float inv = 1.f / (float)heads;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t r = t / d;
+        const int c = (int)(t - r * d);
+        float s = 0.f;
+        for (int hh = 0; hh < heads; ++hh) s += to_f32(x[r * ldx + (int64_t)hh * d + c]);
+        out[r * ldo + c] = from_f32<T>(s * inv);
+    }
+}
+
+// gnum = g/den ; gden = -(g.o)/den
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kRowBlock) attn_bwd_prep_kernel(const T* __restrict__ g, const T* __restrict__ o, int64_t ld,
+                                                                   int64_t ld_o, const float* __restrict__ den, int64_t rows, int d, int chunks,
+                                                                   int lpr_log2, float gscale, T* __restrict__ gnum, int64_t ld_gnum,
+                                                                   float* __restrict__ gden) {
+    constexpr int VN = Vec16<T>::N;
+    Lane<T, CPL> L(chunks, lpr_log2);
+    for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
+        const int64_t r = rb + L.grp;
+        const bool live = r < rows;
+        float gg[CPL][VN], oo[CPL][VN];
+        float inv = 0.f;
+        if (live) {
+            L.load(g, ld, r, gg);
+            L.load(o, ld_o, r, oo);
+            inv = gscale / den[r];
+        } else {
+            SGF_ZERO(gg) SGF_ZERO(oo)
+        }
+        float s = 0.f;
+        SGF_FOR_ELEMS { s += gg[c][i] * oo[c][i]; gg[c][i] *= inv; }
+        s = L.row_sum(s);
+        if (live) {
+            L.store(gnum, ld_gnum, r, gg);
+            if (L.sub == 0) gden[r] = -s * inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny h x h glue of the linear attention (one block per row of the output operand)
+__device__ __forceinline__ void store_operand(__nv_bfloat16* base, int64_t ld, int64_t plane_ld, int r, int c, float v) {
+    __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+    base[r * ld + c] = p0;
+    if (plane_ld > 0) {
+        float r1 = v - __bfloat162float(p0);
+        __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+        base[r * ld + plane_ld + c] = p1;
+        base[r * ld + 2 * plane_ld + c] = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+    }
+}
+
+// scal[0]=1/nq scal[1]=1/nk scal[2]=1/(nq*nk)
+__global__ void attn_prepare_fwd_kernel(const float* __restrict__ s_raw, const float* __restrict__ z_raw, const float* __restrict__ nq2v,
+                                        int nq2_len, const float* __restrict__ nk2v, int nk2_len, int m, int d,
+                                        __nv_bfloat16* __restrict__ bmat, int64_t ld_bmat, __nv_bfloat16* __restrict__ btail,
+                                        int64_t ld_btail, int64_t plane_ld, float* __restrict__ scal) {
+    __shared__ float s_inv;
+    if (threadIdx.x < 32) {
+        float a = 0.f, b = 0.f;
+        for (int i = threadIdx.x; i < nq2_len; i += 32) a += nq2v[i];
+        for (int i = threadIdx.x; i < nk2_len; i += 32) b += nk2v[i];
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (threadIdx.x == 0) {
+            float inq = rsqrtf(a), ink = rsqrtf(b);
+            s_inv = inq * ink;
+            if (blockIdx.x == 0) { scal[0] = inq; scal[1] = ink; scal[2] = inq * ink; scal[3] = 0.f; }
+        }
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    const int row = blockIdx.x;  // output row: d index for bmat rows [0,d), tail rows [d, d+16)
+    if (row < d) {
+        for (int mm = threadIdx.x; mm < m; mm += blockDim.x) store_operand(bmat, ld_bmat, plane_ld, row, mm, s_raw[(int64_t)mm * d + row] * inv);
+    } else {
+        const int tr = row - d;
+        for (int mm = threadIdx.x; mm < m; mm += blockDim.x) store_operand(btail, ld_btail, plane_ld, tr, mm, tr == 0 ? z_raw[mm] * inv : 0.f);
+    }
+}
+
+// Backward glue (written for raw q,k and raw partials):
+//   alpha = inq*ink (raw partials S' = k^T v, z' = k^T 1, dS_raw = q^T gnum, dz_raw = q^T gden)
+//   b_dq[m, d]  = S'[m,d]               (B of dq~ = gnum . S^T, scaled by alpha in the epilogue)
+//   b_dv[d, m]  = dS_raw[m,d]           (B of dv  = k . dS, scaled by alpha)
+//   b_dk[m, d]  = dS_raw[m,d]           (B of dk~ = v . dS^T, scaled by alpha)
+//   r1_col[m]   = alpha * z'[m]         (rank-1 term gden (x) z of dq)
+//   dk_bias[m]  = alpha * dz_raw[m]
+//   scal_bwd[0] = alpha, [1] = -c*inq^2, [2] = -c*ink^2, [3] = c     with c = alpha * (<dS_raw,S'> + <dz_raw,z'>)
+__global__ void attn_prepare_bwd_kernel(const float* __restrict__ s_raw, const float* __restrict__ z_raw, const float* __restrict__ ds_raw,
+                                        const float* __restrict__ dz_raw, const float* __restrict__ scal_fwd, int m, int d,
+                                        __nv_bfloat16* __restrict__ b_dq, int64_t ld_b_dq, __nv_bfloat16* __restrict__ b_dv,
+                                        int64_t ld_b_dv, __nv_bfloat16* __restrict__ b_dk, int64_t ld_b_dk, int64_t plane_ld_d,
+                                        int64_t plane_ld_m, float* __restrict__ r1_col, float* __restrict__ dk_bias,
+                                        float* __restrict__ scal_bwd) {
+    const float alpha = scal_fwd[2];
+    const int row = blockIdx.x;  // over m
+    if (row < m) {
+        for (int dd = threadIdx.x; dd < d; dd += blockDim.x) {
+            float sv = s_raw[(int64_t)row * d + dd], dsv = ds_raw[(int64_t)row * d + dd];
+            store_operand(b_dq, ld_b_dq, plane_ld_d, row, dd, sv);
+            store_operand(b_dk, ld_b_dk, plane_ld_d, row, dd, dsv);
+            store_operand(b_dv, ld_b_dv, plane_ld_m, dd, row, dsv);
+        }
+        if (threadIdx.x == 0) { r1_col[row] = alpha * z_raw[row]; dk_bias[row] = alpha * dz_raw[row]; }
+    } else {
+        // last block: the scalar c
+        __shared__ float red[32];
+        float acc = 0.f;
+        for (int64_t i = threadIdx.x; i < (int64_t)m * d; i += blockDim.x) acc += s_raw[i] * ds_raw[i];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) acc += z_raw[i] * dz_raw[i];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) {
+                float inq = scal_fwd[0], ink = scal_fwd[1];
+                float c = alpha * v;  // <dS,S> + <dz,z> with dS = inq*dS_raw, S = ink*S'
+                scal_bwd[0] = alpha;
+                scal_bwd[1] = -c * inq * inq;
+                scal_bwd[2] = -c * ink * ink;
+                scal_bwd[3] = c;
+            }
+        }
+    }
+}
+
+}  // namespace sgf
+
+using namespace sgf;
+
+#define SGF_DISPATCH_T_CPL(dtype, cpl, KERNEL_CALL)                                                        \
+    do {                                                                                                   \
+        if ((dtype) == 0) {                                                                                \
+            using T = float;                                                                               \
+            switch (cpl) {                                                                                 \
+                case 1: { constexpr int CPL = 1; KERNEL_CALL; } break;                                     \
+                case 2: { constexpr int CPL = 2; KERNEL_CALL; } break;                                     \
+                case 3: { constexpr int CPL = 3; KERNEL_CALL; } break;                                     \
+                default: { constexpr int CPL = 4; KERNEL_CALL; } break;                                    \
+            }                                                                                              \
+        } else {                                                                                           \
+            using T = __nv_bfloat16;                                                                       \
+            switch (cpl) {                                                                                 \
+                case 1: { constexpr int CPL = 1; KERNEL_CALL; } break;                                     \
+                case 2: { constexpr int CPL = 2; KERNEL_CALL; } break;                                     \
+                case 3: { constexpr int CPL = 3; KERNEL_CALL; } break;                                     \
+                default: { constexpr int CPL = 4; KERNEL_CALL; } break;                                    \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+
+static inline bool geom_for(int dtype, int h, RowGeom& g) {
+    if (dtype == 0) return make_geom<float>(h, g);
+    if (dtype == 1) return make_geom<__nv_bfloat16>(h, g);
+    return false;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool ld_ok(int dtype, int64_t ld) { return ld % (dtype == 0 ? 4 : 8) == 0; }
+
+extern "C" int sgf_colstats(const void* x, int64_t ldx, int64_t rows, int h, int dtype, const float* w, float* sum, float* sumsq,
+                            void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(x) || !ld_ok(dtype, ldx) || rows < 0) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (colstats_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                         (const T*)x, ldx, rows, h, g.chunks, g.lpr_log2, w, sum, sumsq)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_ln_fwd(const void* x, const void* r, int64_t ld, int64_t rows, int h, int dtype, float a, float b,
+                          const float* gamma, const float* beta, int use_ln, int use_relu, float p, uint64_t seed, void* y,
+                          float* stats, void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(x) || !aligned16(y) || !aligned16(r) || !ld_ok(dtype, ld) || rows < 0) return SGF_ERR_ARG;
+    if (use_ln && (!gamma || !beta)) return SGF_ERR_ARG;
+    if (p < 0.f || p >= 1.f) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (ln_fwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, 0, st>>>(
+                                         (const T*)x, (const T*)r, ld, rows, h, g.chunks, g.lpr_log2, a, b, gamma, beta, use_ln,
+                                         use_relu, p, seed, (T*)y, stats)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_ln_bwd(const void* dy, const void* x, const void* r, int64_t ld, int64_t rows, int h, int dtype, float a,
+                          float b, const float* gamma, const float* beta, const float* stats, int use_ln, int use_relu, float p,
+                          uint64_t seed, float gscale, void* dx, void* dr, float* dgamma, float* dbeta, void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(x) || !aligned16(dy) || !aligned16(dx) || !aligned16(r) || !aligned16(dr) ||
+        !ld_ok(dtype, ld) || rows < 0)
+        return SGF_ERR_ARG;
+    if (use_ln && (!gamma || !beta || !stats)) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (ln_bwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                         (const T*)dy, (const T*)x, (const T*)r, ld, rows, h, g.chunks, g.lpr_log2, a, b, gamma, beta,
+                                         stats, use_ln, use_relu, p, seed, gscale, (T*)dx, (T*)dr, dgamma, dbeta)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_bn_finalize(const float* sum, const float* sumsq, int64_t rows, int h, float eps, float momentum,
+                               const float* zbias, float* mean, float* rstd, float* running_mean, float* running_var, void* stream) {
+    if (h <= 0 || !mean || !rstd) return SGF_ERR_ARG;
+    if (!sum && (!running_mean || !running_var)) return SGF_ERR_ARG;
+    if (sum && (!sumsq || rows <= 0)) return SGF_ERR_ARG;
+    bn_finalize_kernel<<<(h + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, rows, h, eps, momentum, zbias, mean, rstd,
+                                                                          running_mean, running_var);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_bn_fwd(const void* z, const void* res, const void* mix, int64_t ld, int64_t rows, int h, int dtype,
+                          const float* mean, const float* rstd, const float* gamma, const float* beta, const float* zbias,
+                          int use_bn, int use_relu, float p, uint64_t seed, float gw, const float* row_scale, void* y,
+                          void* y_scaled, void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(z) || !aligned16(res) || !aligned16(mix) || !aligned16(y) || !aligned16(y_scaled) ||
+        !ld_ok(dtype, ld) || rows < 0)
+        return SGF_ERR_ARG;
+    if (use_bn && (!mean || !rstd || !gamma || !beta)) return SGF_ERR_ARG;
+    if (y_scaled && !row_scale) return SGF_ERR_ARG;
+    if (p < 0.f || p >= 1.f) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_fwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, 0, st>>>(
+                                         (const T*)z, (const T*)res, (const T*)mix, ld, rows, h, g.chunks, g.lpr_log2, mean, rstd,
+                                         gamma, beta, zbias, use_bn, use_relu, p, seed, gw, row_scale, (T*)y, (T*)y_scaled)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld, int64_t rows,
+                                 int h, int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                 const float* zbias, int use_bn, int use_relu, float p, uint64_t seed, float gscale, float* sums,
+                                 void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(dy) || !aligned16(dy2) || !aligned16(z) || !ld_ok(dtype, ld) || rows < 0 || !sums ||
+        (!dy && !dy2))
+        return SGF_ERR_ARG;
+    if (use_bn && (!mean || !rstd || !gamma || !beta)) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_bwd_kernel<T, CPL, false><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                         (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
+                                         rstd, gamma, beta, zbias, use_bn, use_relu, 1, p, seed, gscale, sums, (T*)nullptr,
+                                         (T*)nullptr, 0, (float*)nullptr, (const float*)nullptr)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld, int64_t rows,
+                                int h, int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                const float* zbias, int use_bn, int use_relu, int training, float p, uint64_t seed, float gscale,
+                                const float* sums, void* dz, void* dres, int dres_accumulate, float* dz_colsum,
+                                const float* out_row_scale, void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(dy) || !aligned16(dy2) || !aligned16(z) || !aligned16(dz) || !aligned16(dres) ||
+        !ld_ok(dtype, ld) || rows < 0 || (!dy && !dy2))
+        return SGF_ERR_ARG;
+    if (use_bn && (!mean || !rstd || !gamma || !beta)) return SGF_ERR_ARG;
+    if (use_bn && training && !sums) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_bwd_kernel<T, CPL, true><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                         (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
+                                         rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale,
+                                         const_cast<float*>(sums), (T*)dz, (T*)dres, dres_accumulate, dz_colsum, out_row_scale)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+static inline int ew_grid(int64_t total) {
+    int64_t b = (total + kRowBlock - 1) / kRowBlock;
+    int64_t cap = (int64_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int sgf_axpby(const void* x, int64_t ldx, int x_dtype, const void* y, int64_t ldy, int y_dtype, float a, float b,
+                         const float* row_scale, void* out, int64_t ldo, int out_dtype, int64_t rows, int h, void* stream) {
+    if (!x || !out || rows < 0 || h <= 0 || (y && y_dtype != x_dtype)) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ew_grid(rows * ((h + 3) / 4));
+    if (x_dtype == 0 && out_dtype == 0)
+        axpby_kernel<float, float><<<grid, kRowBlock, 0, st>>>((const float*)x, ldx, (const float*)y, ldy, a, b, row_scale, (float*)out, ldo, rows, h);
+    else if (x_dtype == 0 && out_dtype == 1)
+        axpby_kernel<float, __nv_bfloat16><<<grid, kRowBlock, 0, st>>>((const float*)x, ldx, (const float*)y, ldy, a, b, row_scale, (__nv_bfloat16*)out, ldo, rows, h);
+    else if (x_dtype == 1 && out_dtype == 0)
+        axpby_kernel<__nv_bfloat16, float><<<grid, kRowBlock, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)y, ldy, a, b, row_scale, (float*)out, ldo, rows, h);
+    else if (x_dtype == 1 && out_dtype == 1)
+        axpby_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kRowBlock, 0, st>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)y, ldy, a, b, row_scale, (__nv_bfloat16*)out, ldo, rows, h);
+    else
+        return SGF_ERR_ARG;
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, int cols, int transpose, void* dst,
+                                int64_t ld_dst, int kp, int64_t plane_ld, float* colsum, void* stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || kp <= 0) return SGF_ERR_ARG;
+    const int64_t cols_out = transpose ? rows : cols;
+    if (kp < cols_out || (plane_ld > 0 && plane_ld < kp) || ld_dst < (plane_ld > 0 ? 2 * plane_ld + kp : kp)) return SGF_ERR_ARG;
+    if (colsum && cols > 8192) return SGF_ERR_UNSUPPORTED;
+    const int64_t rows_out = transpose ? cols : rows;
+    pack_operand_kernel<<<ew_grid(rows_out * kp), kRowBlock, colsum ? cols * sizeof(float) : 0, (cudaStream_t)stream>>>(
+        src, ld_src, rows, cols, transpose, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, colsum);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_attn_combine_scal(float* scal_bwd, int heads, int stride, const float* scal_fwd, void* stream) {
+    if (!scal_bwd || !scal_fwd || heads <= 0 || stride < 4) return SGF_ERR_ARG;
+    attn_combine_scal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scal_bwd, heads, stride, scal_fwd);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_head_mean(const void* x, int64_t ldx, int64_t rows, int heads, int d, int dtype, void* out, int64_t ldo, void* stream) {
+    if (!x || !out || rows < 0 || heads <= 0 || d <= 0) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0) head_mean_kernel<float><<<ew_grid(rows * d), kRowBlock, 0, st>>>((const float*)x, ldx, rows, heads, d, (float*)out, ldo);
+    else if (dtype == 1) head_mean_kernel<__nv_bfloat16><<<ew_grid(rows * d), kRowBlock, 0, st>>>((const __nv_bfloat16*)x, ldx, rows, heads, d, (__nv_bfloat16*)out, ldo);
+    else return SGF_ERR_ARG;
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_attn_bwd_prep(const void* g, int64_t ld, const void* o, int64_t ld_o, const float* den, int64_t rows, int d,
+                                 int dtype, float gscale, void* gnum, int64_t ld_gnum, float* gden, void* stream) {
+    RowGeom gm;
+    if (!geom_for(dtype, d, gm) || !aligned16(g) || !aligned16(o) || !aligned16(gnum) || !ld_ok(dtype, ld) || !ld_ok(dtype, ld_o) ||
+        !ld_ok(dtype, ld_gnum) || !den || !gden || rows < 0)
+        return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL(dtype, gm.cpl, (attn_bwd_prep_kernel<T, CPL><<<row_grid(rows, gm), kRowBlock, 0, st>>>(
+                                          (const T*)g, (const T*)o, ld, ld_o, den, rows, d, gm.chunks, gm.lpr_log2, gscale, (T*)gnum, ld_gnum, gden)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_attn_prepare_fwd(const float* s_raw, const float* z_raw, const float* nq2, int nq2_len, const float* nk2,
+                                    int nk2_len, int m, int d, void* bmat, int64_t ld_bmat, void* btail, int64_t ld_btail,
+                                    int64_t plane_ld, float* scal, void* stream) {
+    if (!s_raw || !z_raw || !nq2 || !nk2 || !bmat || !btail || !scal || m <= 0 || d <= 0) return SGF_ERR_ARG;
+    attn_prepare_fwd_kernel<<<d + 16, 128, 0, (cudaStream_t)stream>>>(s_raw, z_raw, nq2, nq2_len, nk2, nk2_len, m, d,
+                                                                      (__nv_bfloat16*)bmat, ld_bmat, (__nv_bfloat16*)btail, ld_btail,
+                                                                      plane_ld, scal);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_attn_prepare_bwd(const float* s_raw, const float* z_raw, const float* ds_raw, const float* dz_raw,
+                                    const float* scal_fwd, int m, int d, void* b_dq, int64_t ld_b_dq, void* b_dv, int64_t ld_b_dv,
+                                    void* b_dk, int64_t ld_b_dk, int64_t plane_ld_d, int64_t plane_ld_m, float* r1_col,
+                                    float* dk_bias, float* scal_bwd, void* stream) {
+    if (!s_raw || !z_raw || !ds_raw || !dz_raw || !scal_fwd || !b_dq || !b_dv || !b_dk || !r1_col || !dk_bias || !scal_bwd ||
+        m <= 0 || d <= 0)
+        return SGF_ERR_ARG;
+    attn_prepare_bwd_kernel<<<m + 1, 128, 0, (cudaStream_t)stream>>>(s_raw, z_raw, ds_raw, dz_raw, scal_fwd, m, d,
+                                                                     (__nv_bfloat16*)b_dq, ld_b_dq, (__nv_bfloat16*)b_dv, ld_b_dv,
+                                                                     (__nv_bfloat16*)b_dk, ld_b_dk, plane_ld_d, plane_ld_m, r1_col,
+                                                                     dk_bias, scal_bwd);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}

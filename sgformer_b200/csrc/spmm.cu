@@ -1,0 +1,157 @@
+// K6 / K7 — CSR SpMM  y[r,:] = row_scale[r] * sum_{j in row r} x[col[j], :]
+//
+// Replaces torch_sparse.matmul(adj, x) (reference large/ours.py:34, 100M/ours.py:80; torch_sparse 0.6.10 spmm_kernel:
+// fp32, int64 indices, value array, one warp per row x 32 feature columns) and its autograd transpose.
+//
+// Design (pure HBM-bound gather, no tensor cores):
+//   * no value array: Â = D^-1/2 A D^-1/2 is applied as a row pre-scale in the producer of x and `row_scale` here,
+//     which removes 4 B/nnz and one dependent gather;
+//   * int32 column ids, int64 rowptr (nnz may exceed 2^31);
+//   * one warp per output row; a feature row is split into 16-byte chunks, `lpr` lanes cover one neighbour row with
+//     128-bit ld.global.nc.L1::no_allocate loads (512 B row at h=256 bf16 = one fully coalesced warp load); when a row
+//     needs fewer than 32 lanes the warp gathers 32/lpr neighbours at once and folds them with shuffles at the end;
+//   * column ids are read 32 at a time (one coalesced 128 B load) and broadcast with __shfl_sync;
+//   * kUnroll neighbour rows are in flight per lane group before the fp32 accumulation (memory-level parallelism:
+//     >= 64 KB in flight per SM at 32 resident warps, above the ~44 KB latency-bandwidth product of one SM's HBM share).
+// Algorithmic bytes per launch: nnz*4 + (n+1)*8 + nnz*h*b + n*h*b.
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/sgformer_b200.h"
+
+namespace sgf {
+
+constexpr int kSpmmBlock = 256;
+constexpr int kUnroll = 4;
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kSpmmBlock, 4)
+spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
+                 const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int lpr = 1 << lpr_log2;
+    const int groups = 32 >> lpr_log2;
+    const int grp = lane >> lpr_log2;
+    const int sub = lane & (lpr - 1);
+    const int64_t warp0 = ((int64_t)blockIdx.x * kSpmmBlock + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kSpmmBlock) >> 5;
+
+    // per-lane chunk offsets (elements) and validity
+    int coff[CPL];
+    bool cval[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int ch = sub + c * lpr;
+        cval[c] = ch < chunks;
+        coff[c] = ch * VN;
+    }
+
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        const int64_t s = rowptr[r];
+        const int64_t e = rowptr[r + 1];
+        float acc[CPL][VN];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
+
+        for (int64_t base = s; base < e; base += 32) {
+            const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+            const int my_idx = lane < cnt ? ldg_nc_na_s32(col + base + lane) : -1;
+            for (int j0 = 0; j0 < cnt; j0 += groups * kUnroll) {
+                uint4 v[kUnroll][CPL];
+                int nb[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    int j = j0 + u * groups + grp;
+                    int t = __shfl_sync(0xffffffffu, my_idx, j & 31);
+                    nb[u] = j < cnt ? t : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
+                        else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        float f[VN];
+                        Vec16<T>::unpack(v[u][c], f);
+#pragma unroll
+                        for (int i = 0; i < VN; ++i) acc[c][i] += f[i];
+                    }
+            }
+        }
+        // fold the neighbour groups
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], o);
+        }
+        const float rs = row_scale ? row_scale[r] : 1.0f;
+        if (grp == 0) {
+            T* dst = y + r * ldy;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (!cval[c]) continue;
+                float f[VN];
+#pragma unroll
+                for (int i = 0; i < VN; ++i) f[i] = acc[c][i] * rs;
+                stg_na(dst + coff[c], Vec16<T>::pack(f));
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
+                       void* y, int64_t ldy, int64_t n_rows, int h, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    if (h % VN != 0 || ldx % VN != 0 || ldy % VN != 0) return SGF_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return SGF_ERR_ARG;
+    const int chunks = h / VN;
+    int lpr_log2 = 0;
+    while ((1 << lpr_log2) < chunks && lpr_log2 < 5) ++lpr_log2;
+    const int lpr = 1 << lpr_log2;
+    const int cpl = (chunks + lpr - 1) / lpr;
+    if (n_rows == 0) return SGF_OK;
+    int64_t warps_needed = n_rows;
+    int64_t blocks = (warps_needed * 32 + kSpmmBlock - 1) / kSpmmBlock;
+    int64_t cap = (int64_t)num_sms() * 4 * 8;  // 8 waves of 4 resident CTAs per SM, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    const T* xp = static_cast<const T*>(x);
+    T* yp = static_cast<T*>(y);
+#define SGF_SPMM_CASE(N)                                                                                              \
+    case N:                                                                                                           \
+        spmm_rows_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy,      \
+                                                                        n_rows, chunks, lpr_log2);                     \
+        break;
+    switch (cpl) {
+        SGF_SPMM_CASE(1)
+        SGF_SPMM_CASE(2)
+        SGF_SPMM_CASE(3)
+        SGF_SPMM_CASE(4)
+        default: return SGF_ERR_UNSUPPORTED;  // rows wider than 2 KB
+    }
+#undef SGF_SPMM_CASE
+    SGF_LAUNCH_CHECK();
+    count_launch();
+    return SGF_OK;
+}
+
+}  // namespace sgf
+
+extern "C" int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
+                        void* y, int64_t ldy, int64_t n_rows, int h, int dtype, void* stream) {
+    if (!rowptr || n_rows < 0 || h <= 0 || (n_rows > 0 && (!x || !y))) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0) return sgf::launch_spmm<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, st);
+    if (dtype == 1) return sgf::launch_spmm<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, st);
+    return SGF_ERR_ARG;
+}

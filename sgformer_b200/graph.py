@@ -1,0 +1,80 @@
+"""Graph structure cache: CSR of the GCN aggregation pattern (+ lazily its transpose) built once per edge list.
+
+The reference rebuilds degree -> edge weights -> sort -> CSR inside every GraphConvLayer.forward
+(/root/reference/large/ours.py:26-33); it is graph-constant, so it is hoisted here and keyed on the edge_index tensor."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+
+from . import kernels as K
+
+Tensor = torch.Tensor
+
+
+def _is_symmetric(edge_index: Tensor, n: int) -> bool:
+    """Multiset equality of {(r,c)} and {(c,r)} through an order-independent 64-bit hash sum (one device sync)."""
+    r, c = edge_index[0], edge_index[1]
+    k1, k2 = r * n + c, c * n + r
+
+    def hsum(k):
+        x = k * -7046029254386353131          # 0x9E3779B97F4A7C15 as int64, wraps
+        x = x ^ (x >> 29)
+        x = x * -4658895280553007687          # 0xBF58476D1CE4E5B9
+        return (x ^ (x >> 32)).sum()
+
+    return bool((hsum(k1) == hsum(k2)).item())
+
+
+class Graph:
+    """rowptr int64 [n+1], col int32 [nnz] (rows = edge targets, sorted columns, duplicates kept), dinv fp32 [n].
+    self_loop_mode 0: large/100M GraphConv; 1: PyG gcn_norm (medium GCN)."""
+
+    def __init__(self, edge_index: Tensor, n: int, self_loop_mode: int = 0):
+        if not edge_index.is_cuda:
+            raise RuntimeError("Graph needs a CUDA edge_index (no CPU fallback)")
+        self.n = int(n)
+        self.self_loop_mode = self_loop_mode
+        self.edge_index = edge_index
+        self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True)
+        self._t: Optional[Tuple[Tensor, Tensor]] = None
+
+    @property
+    def nnz(self) -> int:
+        return self.col.numel()
+
+    def transpose(self) -> Tuple[Tensor, Tensor]:
+        """CSR of the transposed pattern (rows = edge sources) for the backward SpMM; shares storage when the edge
+        list is symmetric (the usual case after to_undirected)."""
+        if self._t is None:
+            if _is_symmetric(self.edge_index, self.n):
+                self._t = (self.rowptr, self.col)
+            else:
+                rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False)
+                self._t = (rp, cl)
+        return self._t
+
+
+_CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
+_CACHE_MAX = 4
+
+
+def get_graph(edge_index: Tensor, n: int, self_loop_mode: int = 0) -> Graph:
+    """Cached Graph for this edge_index tensor (identity: storage pointer, shape, version)."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index, int(n),
+           self_loop_mode)
+    g = _CACHE.get(key)
+    if g is not None and g.edge_index is edge_index:
+        _CACHE.move_to_end(key)
+        return g
+    g = Graph(edge_index, n, self_loop_mode)
+    _CACHE[key] = g
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return g
+
+
+def clear_cache():
+    _CACHE.clear()

@@ -1,0 +1,488 @@
+"""Functional (autograd-free) Python wrappers over the C-ABI kernels.
+
+Every function takes CUDA torch tensors, validates layout, and launches on torch's current stream.
+Nothing here touches CPU tensors: a non-CUDA tensor raises — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, EPI_AFFINE, EPI_ATTN_APPLY, F32, GemmNtArgs, GemmTnArgs, check
+
+Tensor = torch.Tensor
+_tls = threading.local()
+
+
+def lib():
+    return _lib.load()
+
+
+def _use(t: Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("sgformer_b200 kernels need CUDA tensors (no CPU fallback); got device " + str(t.device))
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if getattr(_tls, "dev", None) != idx:
+        check(lib().sgf_set_device(idx), "sgf_set_device")
+        _tls.dev = idx
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def dcode(t_or_dtype) -> int:
+    dt = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {dt}")
+
+
+def _mat(t: Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a row-major 2-D tensor, got shape {tuple(t.shape)} stride {t.stride()}")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def _f32vec(t: Optional[Tensor], n: int, name: str):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+        raise ValueError(f"{name}: expected contiguous fp32 with >= {n} elements")
+    return t
+
+
+def ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def alloc_act(rows: int, h: int, dtype, device) -> Tensor:
+    """[rows, h] activation whose pitch keeps rows 16-byte aligned."""
+    mult = 8 if dtype == torch.bfloat16 else 4
+    hp = ceil_to(h, mult)
+    buf = torch.empty((rows, hp), dtype=dtype, device=device)
+    return buf[:, :h] if hp != h else buf
+
+
+def new_like(x: Tensor) -> Tensor:
+    """Uninitialised activation with the same shape and pitch as the 2-D row-major tensor x."""
+    rows, h, ld = _mat(x, "x")
+    if ld == h:
+        return torch.empty((rows, h), dtype=x.dtype, device=x.device)
+    return torch.empty((rows, ld), dtype=x.dtype, device=x.device)[:, :h]
+
+
+# ------------------------------------------------------------------------------------------------
+# graph structure
+# ------------------------------------------------------------------------------------------------
+def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mode: int = 0, want_dinv: bool = True):
+    """-> (rowptr int64 [n+1], col int32 [nnz'], dinv fp32 [n] | None).  See sgf_csr_build."""
+    _use(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must be int64 [2, nnz]")
+    ei = edge_index.contiguous()
+    nnz = ei.shape[1]
+    dev = ei.device
+    cap = nnz + (n if self_loop_mode == 1 else 0)
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    dinv = torch.empty(max(n, 1), dtype=torch.float32, device=dev) if (want_dinv and not by_source) else None
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_csr_build_ws_bytes(nnz, n, C.byref(nbytes)), "sgf_csr_build_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    check(lib().sgf_csr_build(_p(ei), nnz, n, int(by_source), self_loop_mode, _p(rowptr), _p(col), _p(dinv), _p(ws),
+                              nbytes.value, _stream()), "sgf_csr_build")
+    if self_loop_mode == 1:
+        total = int(rowptr[n].item())
+        col = col[:total]
+    else:
+        col = col[:nnz]
+    return rowptr, col, (dinv[:n] if dinv is not None else None)
+
+
+def subgraph(edge_index: Tensor, n: int, subset: Tensor) -> Tensor:
+    """Induced subgraph with relabelling; returns int64 [2, nnz_sub] in input edge order (PyG `subgraph` semantics)."""
+    _use(edge_index)
+    ei = edge_index.contiguous()
+    subset = subset.contiguous().to(torch.int64)
+    nnz = ei.shape[1]
+    dev = ei.device
+    node_map = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    out = torch.empty((2, max(nnz, 1)), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_subgraph_ws_bytes(nnz, n, C.byref(nbytes)), "sgf_subgraph_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    check(lib().sgf_subgraph(_p(ei), nnz, n, _p(subset), subset.numel(), _p(node_map), _p(out), _p(count), _p(ws),
+                             nbytes.value, _stream()), "sgf_subgraph")
+    k = int(count.item())
+    return out[:, :k]
+
+
+def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    _use(x)
+    n = rowptr.numel() - 1
+    rows, h, ldx = _mat(x, "x")
+    if out is None:
+        out = alloc_act(n, h, x.dtype, x.device)
+    _, ho, ldy = _mat(out, "out")
+    if ho != h or out.dtype != x.dtype:
+        raise ValueError("spmm: out shape/dtype mismatch")
+    check(lib().sgf_spmm(_p(rowptr), _p(col), _p(_f32vec(row_scale, n, "row_scale")), _p(x), ldx, _p(out), ldy, n, h,
+                         dcode(x), _stream()), "sgf_spmm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core operands
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Operand:
+    """bf16 matrix [rows, k] laid out for TMA: `planes` (1 or 3) copies side by side along K, each `kp` wide."""
+    data: Tensor
+    rows: int
+    k: int
+    kp: int
+    planes: int
+
+    @property
+    def ld(self) -> int:
+        return self.data.stride(0)
+
+    @property
+    def cols(self) -> int:
+        return self.kp * self.planes if self.planes > 1 else self.k
+
+
+# plane pairs of the bf16x3 product, smallest terms first
+_PAIRS3 = [(0, 2), (2, 0), (1, 1), (0, 1), (1, 0), (0, 0)]
+
+
+def operand_from_bf16(x: Tensor) -> Operand:
+    rows, k, ld = _mat(x, "operand")
+    if x.dtype != torch.bfloat16 or ld % 8 != 0 or x.data_ptr() % 16 != 0:
+        raise ValueError("bf16 operand must be 16-byte aligned with a pitch multiple of 8")
+    return Operand(x, rows, k, k, 1)
+
+
+def pack_operand(src: Tensor, transpose: bool = False, planes: int = 1, colsum: Optional[Tensor] = None) -> Operand:
+    """fp32 [r, c] -> bf16 Operand ([c, r] if transpose).  planes=3: bf16x3 split (fp32-accurate products)."""
+    _use(src)
+    if src.dtype != torch.float32:
+        raise TypeError("pack_operand expects fp32")
+    r, c, ld = _mat(src, "src")
+    rows_out, cols_out = (c, r) if transpose else (r, c)
+    kp = ceil_to(cols_out, 64) if planes == 3 else ceil_to(cols_out, 8)
+    dst = torch.empty((rows_out, kp * planes), dtype=torch.bfloat16, device=src.device)
+    check(lib().sgf_pack_operand(_p(src), ld, r, c, int(transpose), _p(dst), dst.stride(0), kp, kp if planes == 3 else 0,
+                                 _p(colsum), _stream()), "sgf_pack_operand")
+    return Operand(dst, rows_out, cols_out, kp, planes)
+
+
+def as_operand(x: Tensor, planes: int) -> Operand:
+    """Activation -> operand: bf16 activations are used in place (planes=1); fp32 activations are packed."""
+    if x.dtype == torch.bfloat16:
+        if planes != 1:
+            raise ValueError("bf16 activations only form single-plane operands")
+        return operand_from_bf16(x)
+    return pack_operand(x, False, planes)
+
+
+def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[int, int, int, int, int]], n_out: int,
+            out: Tensor, *, epi: int = EPI_AFFINE, bias: Optional[Tensor] = None, aux: Optional[Tensor] = None,
+            row_scale: Optional[Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
+            alpha_dev: Optional[Tensor] = None, beta_dev: Optional[Tensor] = None, relu: bool = False,
+            accumulate: bool = False, tail: Optional[Operand] = None, nf: float = 0.0, den_out: Optional[Tensor] = None,
+            r1_row: Optional[Tensor] = None, r1_col: Optional[Tensor] = None) -> Tensor:
+    """out[rows, n_out] = epilogue(sum over `pairs` (ai, a_k0, bi, b_k0, klen) of A[ai][:, a_k0:+klen] . B[bi][:, b_k0:+klen]^T).
+
+    Logical K offsets; 3-plane operands expand every pair into the six bf16x3 partial products."""
+    _use(out)
+    rows = A[0].rows
+    args = GemmNtArgs()
+    if len(A) > _lib.SGF_MAX_SRC or len(B) > _lib.SGF_MAX_SRC:
+        raise ValueError("too many GEMM sources")
+    planes = A[0].planes
+    for o in list(A) + list(B) + ([tail] if tail is not None else []):
+        if o.planes != planes:
+            raise ValueError("all operands of one GEMM must use the same plane count")
+    for i, a in enumerate(A):
+        if a.rows != rows:
+            raise ValueError("A operands must have equal row counts")
+        args.a[i], args.lda[i], args.a_cols[i] = a.data.data_ptr(), a.ld, a.cols
+    for i, b in enumerate(B):
+        if b.rows != n_out:
+            raise ValueError(f"B operand {i} has {b.rows} rows, expected n_out={n_out}")
+        args.b[i], args.ldb[i], args.b_cols[i] = b.data.data_ptr(), b.ld, b.cols
+    args.n_a, args.n_b = len(A), len(B)
+    segs = []
+    combos = _PAIRS3 if planes == 3 else [(0, 0)]
+    for (ai, ak, bi, bk, klen) in pairs:
+        for (pa, pb) in combos:
+            segs.append((ai, pa * A[ai].kp + ak, bi, pb * B[bi].kp + bk, klen))
+    if len(segs) > _lib.SGF_MAX_SEG:
+        raise ValueError("too many GEMM segments")
+    args.n_seg = len(segs)
+    for s, (ai, ak, bi, bk, klen) in enumerate(segs):
+        args.seg_a[s], args.seg_akoff[s], args.seg_b[s], args.seg_bkoff[s], args.seg_klen[s] = ai, ak, bi, bk, klen
+    if tail is not None:
+        if planes != 1 and len(pairs) != 1:
+            raise ValueError("tail with multi-plane operands needs a single pair")
+        args.b_tail, args.ldb_tail = tail.data.data_ptr(), tail.ld
+    args.rows, args.n_out, args.epi = rows, n_out, epi
+    orows, ocols, ldo = _mat(out, "out")
+    if orows != rows or ocols != n_out:
+        raise ValueError(f"out is {tuple(out.shape)}, expected ({rows}, {n_out})")
+    args.out, args.ldo, args.out_dtype = out.data_ptr(), ldo, dcode(out)
+    args.bias = _p(_f32vec(bias, n_out, "bias"))
+    if aux is not None:
+        ar, ac, lda_ = _mat(aux, "aux")
+        if ar != rows or ac != n_out:
+            raise ValueError("aux shape mismatch")
+        args.aux, args.ld_aux, args.aux_dtype = aux.data_ptr(), lda_, dcode(aux)
+    args.row_scale = _p(_f32vec(row_scale, rows, "row_scale"))
+    args.alpha, args.beta = alpha, beta
+    args.alpha_dev, args.beta_dev = _p(alpha_dev), _p(beta_dev)
+    args.relu, args.accumulate = int(relu), int(accumulate)
+    args.nf, args.den_out = nf, _p(_f32vec(den_out, rows, "den_out"))
+    args.r1_row, args.r1_col = _p(_f32vec(r1_row, rows, "r1_row")), _p(_f32vec(r1_col, n_out, "r1_col"))
+    check(lib().sgf_gemm_nt(C.byref(args), _stream()), "sgf_gemm_nt")
+    return out
+
+
+def _tn_once(a: Tensor, lda: int, m: int, b: Tensor, ldb: int, n: int, rows: int, out: Tensor, transpose_out: bool,
+             alpha: float, beta: float, alpha_dev: Optional[Tensor]):
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_gemm_tn_ws_bytes(m, n, rows, C.byref(nbytes)), "sgf_gemm_tn_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 4), dtype=torch.uint8, device=out.device)
+    args = GemmTnArgs()
+    args.a, args.lda, args.m = a.data_ptr(), lda, m
+    args.b, args.ldb, args.n = b.data_ptr(), ldb, n
+    args.rows = rows
+    args.out, args.ldo, args.transpose_out = out.data_ptr(), out.stride(0), int(transpose_out)
+    args.alpha, args.beta, args.alpha_dev = alpha, beta, _p(alpha_dev)
+    args.ws, args.ws_bytes = ws.data_ptr(), nbytes.value
+    check(lib().sgf_gemm_tn(C.byref(args), _stream()), "sgf_gemm_tn")
+
+
+def gemm_tn(A: Operand, B: Operand, out: Tensor, *, transpose_out: bool = False, alpha: float = 1.0, beta: float = 0.0,
+            alpha_dev: Optional[Tensor] = None) -> Tensor:
+    """out[m, n] (fp32; [n, m] if transpose_out) = alpha * A^T B (+ beta*out), A: [rows, m], B: [rows, n].
+    Blocks of 256 features per call; 3-plane operands accumulate the six bf16x3 partial products."""
+    _use(out)
+    if A.rows != B.rows or A.planes != B.planes:
+        raise ValueError("gemm_tn operand mismatch")
+    if out.dtype != torch.float32 or out.stride(-1) != 1:
+        raise ValueError("gemm_tn output must be fp32 row-major")
+    exp = (B.k, A.k) if transpose_out else (A.k, B.k)
+    if tuple(out.shape) != exp:
+        raise ValueError(f"gemm_tn out is {tuple(out.shape)}, expected {exp}")
+    combos = _PAIRS3 if A.planes == 3 else [(0, 0)]
+    for m0 in range(0, A.k, 256):
+        m = min(256, A.k - m0)
+        for n0 in range(0, B.k, 256):
+            n = min(256, B.k - n0)
+            sub = out[n0:n0 + n, m0:m0 + m] if transpose_out else out[m0:m0 + m, n0:n0 + n]
+            for ci, (pa, pb) in enumerate(combos):
+                a_view = A.data[:, pa * A.kp + m0:]
+                b_view = B.data[:, pb * B.kp + n0:]
+                _tn_once(a_view, A.ld, m, b_view, B.ld, n, A.rows, sub, transpose_out, alpha,
+                         beta if ci == 0 else 1.0, alpha_dev)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# row-streaming kernels
+# ------------------------------------------------------------------------------------------------
+def colstats(x: Tensor, w: Optional[Tensor] = None, want_sum: bool = True, want_sumsq: bool = True):
+    _use(x)
+    rows, h, ld = _mat(x, "x")
+    s = torch.zeros(h, dtype=torch.float32, device=x.device) if want_sum else None
+    q = torch.zeros(h, dtype=torch.float32, device=x.device) if want_sumsq else None
+    check(lib().sgf_colstats(_p(x), ld, rows, h, dcode(x), _p(_f32vec(w, rows, "w")), _p(s), _p(q), _stream()),
+          "sgf_colstats")
+    return s, q
+
+
+def _same_ld(ld: int, *ts: Optional[Tensor]):
+    for t in ts:
+        if t is not None and (t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != ld):
+            raise ValueError("row kernels need all activations with the same pitch")
+
+
+def ln_fwd(x: Tensor, r: Optional[Tensor], a: float, b: float, gamma: Optional[Tensor], beta: Optional[Tensor],
+           use_ln: bool, use_relu: bool, p: float, seed: int, want_stats: bool = True):
+    _use(x)
+    rows, h, ld = _mat(x, "x")
+    y = new_like(x)
+    _same_ld(ld, r, y)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if (use_ln and want_stats) else None
+    check(lib().sgf_ln_fwd(_p(x), _p(r), ld, rows, h, dcode(x), a, b, _p(gamma), _p(beta), int(use_ln), int(use_relu), p,
+                           seed, _p(y), _p(stats), _stream()), "sgf_ln_fwd")
+    return y, stats
+
+
+def ln_bwd(dy: Tensor, x: Tensor, r: Optional[Tensor], a: float, b: float, gamma, beta, stats, use_ln: bool,
+           use_relu: bool, p: float, seed: int, gscale: float, want_dr: bool, dgamma: Optional[Tensor],
+           dbeta: Optional[Tensor]):
+    _use(x)
+    rows, h, ld = _mat(x, "x")
+    dx = new_like(x)
+    dr = new_like(x) if want_dr else None
+    _same_ld(ld, dy, r, dx, dr)
+    check(lib().sgf_ln_bwd(_p(dy), _p(x), _p(r), ld, rows, h, dcode(x), a, b, _p(gamma), _p(beta), _p(stats), int(use_ln),
+                           int(use_relu), p, seed, gscale, _p(dx), _p(dr), _p(dgamma), _p(dbeta), _stream()), "sgf_ln_bwd")
+    return dx, dr
+
+
+def bn_finalize(sum_: Optional[Tensor], sumsq: Optional[Tensor], rows: int, h: int, zbias: Optional[Tensor],
+                running_mean: Optional[Tensor], running_var: Optional[Tensor], device, eps: float = 1e-5,
+                momentum: float = 0.1):
+    mean = torch.empty(h, dtype=torch.float32, device=device)
+    rstd = torch.empty(h, dtype=torch.float32, device=device)
+    _use(mean)
+    check(lib().sgf_bn_finalize(_p(sum_), _p(sumsq), rows, h, eps, momentum, _p(zbias), _p(mean), _p(rstd),
+                                _p(running_mean), _p(running_var), _stream()), "sgf_bn_finalize")
+    return mean, rstd
+
+
+def bn_fwd(z: Tensor, res: Optional[Tensor], mix: Optional[Tensor], mean, rstd, gamma, beta, zbias, use_bn: bool,
+           use_relu: bool, p: float, seed: int, gw: float, row_scale: Optional[Tensor], want_y: bool, want_scaled: bool):
+    _use(z)
+    rows, h, ld = _mat(z, "z")
+    y = new_like(z) if want_y else None
+    ys = new_like(z) if want_scaled else None
+    _same_ld(ld, res, mix, y, ys)
+    check(lib().sgf_bn_fwd(_p(z), _p(res), _p(mix), ld, rows, h, dcode(z), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                           _p(zbias), int(use_bn), int(use_relu), p, seed, gw, _p(row_scale), _p(y), _p(ys), _stream()),
+          "sgf_bn_fwd")
+    return y, ys
+
+
+def bn_bwd(dy: Optional[Tensor], dy2: Optional[Tensor], row_scale2: Optional[Tensor], z: Tensor, mean, rstd, gamma, beta,
+           zbias, use_bn: bool, use_relu: bool, training: bool, p: float, seed: int, gscale: float,
+           dres: Optional[Tensor] = None, dres_accumulate: bool = False, want_dz_colsum: bool = False,
+           out_row_scale: Optional[Tensor] = None):
+    """-> (dz, sums [2h] or None (dbeta, dgamma), dz_colsum [h] or None)."""
+    _use(z)
+    rows, h, ld = _mat(z, "z")
+    dz = new_like(z)
+    _same_ld(ld, dy, dy2, dz, dres)
+    sums = None
+    if use_bn and training:
+        sums = torch.zeros(2 * h, dtype=torch.float32, device=z.device)
+        check(lib().sgf_bn_bwd_reduce(_p(dy), _p(dy2), _p(row_scale2), _p(z), ld, rows, h, dcode(z), _p(mean), _p(rstd),
+                                      _p(gamma), _p(beta), _p(zbias), int(use_bn), int(use_relu), p, seed, gscale,
+                                      _p(sums), _stream()), "sgf_bn_bwd_reduce")
+    colsum = torch.zeros(h, dtype=torch.float32, device=z.device) if want_dz_colsum else None
+    check(lib().sgf_bn_bwd_apply(_p(dy), _p(dy2), _p(row_scale2), _p(z), ld, rows, h, dcode(z), _p(mean), _p(rstd),
+                                 _p(gamma), _p(beta), _p(zbias), int(use_bn), int(use_relu), int(training), p, seed,
+                                 gscale, _p(sums), _p(dz), _p(dres), int(dres_accumulate), _p(colsum), _p(out_row_scale),
+                                 _stream()), "sgf_bn_bwd_apply")
+    return dz, sums, colsum
+
+
+def bn_bwd_sums(dy, dy2, row_scale2, z: Tensor, mean, rstd, gamma, beta, zbias, use_bn: bool, use_relu: bool, p: float,
+                seed: int, gscale: float) -> Tensor:
+    """Phase 1 alone: fp32 [2h] = (sum g, sum g*xhat)."""
+    _use(z)
+    rows, h, ld = _mat(z, "z")
+    _same_ld(ld, dy, dy2)
+    sums = torch.zeros(2 * h, dtype=torch.float32, device=z.device)
+    check(lib().sgf_bn_bwd_reduce(_p(dy), _p(dy2), _p(row_scale2), _p(z), ld, rows, h, dcode(z), _p(mean), _p(rstd),
+                                  _p(gamma), _p(beta), _p(zbias), int(use_bn), int(use_relu), p, seed, gscale, _p(sums),
+                                  _stream()), "sgf_bn_bwd_reduce")
+    return sums
+
+
+def axpby(x: Tensor, y: Optional[Tensor], a: float, b: float, out_dtype=None, row_scale: Optional[Tensor] = None,
+          out: Optional[Tensor] = None) -> Tensor:
+    _use(x)
+    rows, h, ldx = _mat(x, "x")
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = alloc_act(rows, h, out_dtype, x.device)
+    ldy = y.stride(0) if y is not None else 0
+    check(lib().sgf_axpby(_p(x), ldx, dcode(x), _p(y), ldy, dcode(y) if y is not None else dcode(x), a, b, _p(row_scale),
+                          _p(out), out.stride(0), dcode(out), rows, h, _stream()), "sgf_axpby")
+    return out
+
+
+def head_mean(x: Tensor, heads: int, d: int) -> Tensor:
+    _use(x)
+    rows, _, ld = _mat(x, "x")
+    out = alloc_act(rows, d, x.dtype, x.device)
+    check(lib().sgf_head_mean(_p(x), ld, rows, heads, d, dcode(x), _p(out), out.stride(0), _stream()), "sgf_head_mean")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# attention glue
+# ------------------------------------------------------------------------------------------------
+def attn_prepare_fwd(s_raw: Tensor, z_raw: Tensor, nq2v: Tensor, nk2v: Tensor, planes: int):
+    """-> (bmat Operand [d, m], btail Operand [16, m], scal fp32 [4])."""
+    _use(s_raw)
+    m, d = s_raw.shape
+    kp = ceil_to(m, 64) if planes == 3 else ceil_to(m, 8)
+    bmat = torch.empty((d, kp * planes), dtype=torch.bfloat16, device=s_raw.device)
+    btail = torch.empty((16, kp * planes), dtype=torch.bfloat16, device=s_raw.device)
+    if kp != m:
+        bmat.zero_()
+        btail.zero_()
+    scal = torch.empty(4, dtype=torch.float32, device=s_raw.device)
+    check(lib().sgf_attn_prepare_fwd(_p(s_raw), _p(z_raw), _p(nq2v), nq2v.numel(), _p(nk2v), nk2v.numel(), m, d, _p(bmat),
+                                     bmat.stride(0), _p(btail), btail.stride(0), kp if planes == 3 else 0, _p(scal),
+                                     _stream()), "sgf_attn_prepare_fwd")
+    return Operand(bmat, d, m, kp, planes), Operand(btail, 16, m, kp, planes), scal
+
+
+def attn_bwd_prep(g: Tensor, o: Tensor, den: Tensor, gscale: float):
+    _use(g)
+    rows, d, ld = _mat(g, "g")
+    _, _, ld_o = _mat(o, "o")
+    gnum = alloc_act(rows, d, g.dtype, g.device)
+    gden = torch.empty(rows, dtype=torch.float32, device=g.device)
+    check(lib().sgf_attn_bwd_prep(_p(g), ld, _p(o), ld_o, _p(den), rows, d, dcode(g), gscale, _p(gnum), gnum.stride(0),
+                                  _p(gden), _stream()), "sgf_attn_bwd_prep")
+    return gnum, gden
+
+
+def attn_prepare_bwd(s_raw: Tensor, z_raw: Tensor, ds_raw: Tensor, dz_raw: Tensor, scal_fwd: Tensor, planes: int,
+                     scal_bwd: Tensor):
+    _use(s_raw)
+    m, d = s_raw.shape
+    kpd = ceil_to(d, 64) if planes == 3 else ceil_to(d, 8)
+    kpm = ceil_to(m, 64) if planes == 3 else ceil_to(m, 8)
+    dev = s_raw.device
+    b_dq = torch.zeros((m, kpd * planes), dtype=torch.bfloat16, device=dev)
+    b_dk = torch.zeros((m, kpd * planes), dtype=torch.bfloat16, device=dev)
+    b_dv = torch.zeros((d, kpm * planes), dtype=torch.bfloat16, device=dev)
+    r1_col = torch.empty(m, dtype=torch.float32, device=dev)
+    dk_bias = torch.empty(m, dtype=torch.float32, device=dev)
+    check(lib().sgf_attn_prepare_bwd(_p(s_raw), _p(z_raw), _p(ds_raw), _p(dz_raw), _p(scal_fwd), m, d, _p(b_dq),
+                                     b_dq.stride(0), _p(b_dv), b_dv.stride(0), _p(b_dk), b_dk.stride(0),
+                                     kpd if planes == 3 else 0, kpm if planes == 3 else 0, _p(r1_col), _p(dk_bias),
+                                     _p(scal_bwd), _stream()), "sgf_attn_prepare_bwd")
+    return (Operand(b_dq, m, d, kpd, planes), Operand(b_dv, d, m, kpm, planes), Operand(b_dk, m, d, kpd, planes), r1_col,
+            dk_bias)
+
+
+def attn_combine_scal(scal_bwd_all: Tensor, heads: int, scal_fwd: Tensor):
+    _use(scal_bwd_all)
+    check(lib().sgf_attn_combine_scal(_p(scal_bwd_all), heads, scal_bwd_all.stride(0), _p(scal_fwd), _stream()),
+          "sgf_attn_combine_scal")
+
+
+def launch_count() -> int:
+    return int(lib().sgf_launch_count())

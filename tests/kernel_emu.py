@@ -1,0 +1,315 @@
+"""torch-CPU emulation of sgformer_b200.kernels — TEST INFRASTRUCTURE ONLY.
+
+Lets the hand-written forward/backward *schedules* of sgformer_b200/engine.py (which kernels run in which order, with
+which scalings and accumulations) be checked against the oracle in the GPU-less build container: tests monkeypatch
+`engine.K` / `functional.K` with this module.  It mirrors the documented semantics of every C-ABI entry point
+(include/sgformer_b200.h) with plain tensor ops; it is never imported by the package and proves nothing about the CUDA
+kernels themselves (those are checked by the `-m gpu` tests against the oracle)."""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+EPI_AFFINE, EPI_ATTN_APPLY = 0, 1
+
+
+def _use(t):
+    pass
+
+
+def ceil_to(x, m):
+    return (x + m - 1) // m * m
+
+
+def alloc_act(rows, h, dtype, device):
+    return torch.zeros((rows, h), dtype=dtype, device=device)
+
+
+def new_like(x):
+    return torch.zeros(x.shape, dtype=x.dtype, device=x.device)
+
+
+def _st(out, val):
+    out.copy_(val.to(out.dtype))
+    return out
+
+
+@dataclass
+class Operand:
+    data: torch.Tensor  # logical fp32 [rows, k]
+    rows: int
+    k: int
+    kp: int
+    planes: int
+
+
+def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True):
+    src, dst = edge_index[0], edge_index[1]
+    if self_loop_mode == 1:
+        keep = src != dst
+        ar = torch.arange(n)
+        src, dst = torch.cat([src[keep], ar]), torch.cat([dst[keep], ar])
+    key, val = (src, dst) if by_source else (dst, src)
+    order = torch.argsort(key * n + val, stable=True)
+    deg = torch.bincount(key, minlength=n)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    d = deg.float()
+    dinv = torch.where(d > 0, (1.0 / d).sqrt(), torch.zeros_like(d)) if (want_dinv and not by_source) else None
+    return rowptr, val[order].to(torch.int32), dinv
+
+
+def spmm(rowptr, col, row_scale, x, out=None):
+    n = rowptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    y = torch.zeros((n, x.shape[1]), dtype=torch.float32).index_add_(0, rows, x.float()[col.long()])
+    if row_scale is not None:
+        y = y * row_scale[:, None]
+    return _st(out if out is not None else alloc_act(n, x.shape[1], x.dtype, x.device), y)
+
+
+def operand_from_bf16(x):
+    return Operand(x.float(), x.shape[0], x.shape[1], x.shape[1], 1)
+
+
+def pack_operand(src, transpose=False, planes=1, colsum=None):
+    if colsum is not None:
+        colsum += src.sum(0)
+    d = (src.t() if transpose else src).contiguous().float()
+    if planes == 1:
+        d = d.bfloat16().float()
+    return Operand(d, d.shape[0], d.shape[1], ceil_to(d.shape[1], 64), planes)
+
+
+def as_operand(x, planes):
+    if x.dtype == torch.bfloat16:
+        return operand_from_bf16(x)
+    return pack_operand(x, False, planes)
+
+
+def gemm_nt(A, B, pairs, n_out, out, *, epi=EPI_AFFINE, bias=None, aux=None, row_scale=None, alpha=1.0, beta=0.0,
+            alpha_dev=None, beta_dev=None, relu=False, accumulate=False, tail=None, nf=0.0, den_out=None, r1_row=None,
+            r1_col=None):
+    acc = 0
+    for (ai, ak, bi, bk, klen) in pairs:
+        acc = acc + A[ai].data[:, ak:ak + klen] @ B[bi].data[:, bk:bk + klen].t()
+    assert acc.shape[1] == n_out
+    if epi == EPI_ATTN_APPLY:
+        den = (A[0].data @ tail.data.t())[:, 0] + nf
+        if den_out is not None:
+            den_out.copy_(den)
+        v = (acc + nf * aux.float()) / den[:, None]
+    else:
+        a = alpha * (float(alpha_dev) if alpha_dev is not None else 1.0)
+        b = beta * (float(beta_dev) if beta_dev is not None else 1.0)
+        v = a * acc
+        if aux is not None:
+            v = v + b * aux.float()
+        if bias is not None:
+            v = v + bias[:n_out]
+        if r1_row is not None:
+            v = v + r1_row[:, None] * r1_col[None, :n_out]
+        if relu:
+            v = v.clamp_min(0)
+        if row_scale is not None:
+            v = v * row_scale[:, None]
+    if accumulate:
+        v = v + out.float()
+    return _st(out, v)
+
+
+def gemm_tn(A, B, out, *, transpose_out=False, alpha=1.0, beta=0.0, alpha_dev=None):
+    r = alpha * (float(alpha_dev) if alpha_dev is not None else 1.0) * (A.data.t() @ B.data)
+    if transpose_out:
+        r = r.t()
+    if beta != 0.0:
+        r = r + beta * out
+    return _st(out, r)
+
+
+def colstats(x, w=None, want_sum=True, want_sumsq=True):
+    xf = x.float()
+    s = (xf * (w[:, None] if w is not None else 1.0)).sum(0) if want_sum else None
+    q = (xf * xf).sum(0) if want_sumsq else None
+    return s, q
+
+
+def _ln_core(x, r, a, b, gamma, beta, use_ln, use_relu):
+    u = a * x.float() + (b * r.float() if r is not None else 0.0)
+    mean = rstd = None
+    xh = u
+    if use_ln:
+        mean = u.mean(1)
+        rstd = (u.var(1, unbiased=False) + 1e-5).rsqrt()
+        xh = (u - mean[:, None]) * rstd[:, None]
+        t = xh * gamma + beta
+    else:
+        t = u
+    return u, xh, t, mean, rstd
+
+
+def ln_fwd(x, r, a, b, gamma, beta, use_ln, use_relu, p, seed, want_stats=True):
+    assert p == 0.0, "emulation supports dropout p=0 only"
+    u, xh, t, mean, rstd = _ln_core(x, r, a, b, gamma, beta, use_ln, use_relu)
+    if use_relu:
+        t = t.clamp_min(0)
+    stats = torch.stack([mean, rstd], 1) if use_ln else None
+    return _st(new_like(x), t), stats
+
+
+def ln_bwd(dy, x, r, a, b, gamma, beta, stats, use_ln, use_relu, p, seed, gscale, want_dr, dgamma, dbeta):
+    u, xh, t, mean, rstd = _ln_core(x, r, a, b, gamma, beta, use_ln, use_relu)
+    g = gscale * dy.float()
+    if use_relu:
+        g = g * (t > 0)
+    if use_ln:
+        dgamma += (g * xh).sum(0)
+        dbeta += g.sum(0)
+        gg = g * gamma
+        du = rstd[:, None] * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+    else:
+        du = g
+    dx = _st(new_like(x), a * du)
+    dr = _st(new_like(x), b * du) if want_dr else None
+    return dx, dr
+
+
+def bn_finalize(sum_, sumsq, rows, h, zbias, running_mean, running_var, device, eps=1e-5, momentum=0.1):
+    if sum_ is not None:
+        m = sum_ / rows
+        var = (sumsq / rows - m * m).clamp_min(0)
+        if zbias is not None:
+            m = m + zbias
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(momentum * m)
+            running_var.mul_(1 - momentum).add_(momentum * var * rows / max(rows - 1, 1))
+        return m, (var + eps).rsqrt()
+    return running_mean.clone(), (running_var + eps).rsqrt()
+
+
+def _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn):
+    zz = z.float() + (zbias if zbias is not None else 0.0)
+    if use_bn:
+        xh = (zz - mean) * rstd
+        return xh, xh * gamma + beta
+    return zz, zz
+
+
+def bn_fwd(z, res, mix, mean, rstd, gamma, beta, zbias, use_bn, use_relu, p, seed, gw, row_scale, want_y, want_scaled):
+    assert p == 0.0
+    _, t = _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn)
+    if use_relu:
+        t = t.clamp_min(0)
+    if res is not None:
+        t = t + res.float()
+    ys = _st(new_like(z), t * row_scale[:, None]) if want_scaled else None
+    if mix is not None:
+        t = gw * t + (1 - gw) * mix.float()
+    y = _st(new_like(z), t) if want_y else None
+    return y, ys
+
+
+def _bn_g(dy, dy2, row_scale2, gscale):
+    g = 0
+    if dy is not None:
+        g = g + dy.float()
+    if dy2 is not None:
+        g = g + dy2.float() * (row_scale2[:, None] if row_scale2 is not None else 1.0)
+    return gscale * g
+
+
+def bn_bwd_sums(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, use_relu, p, seed, gscale):
+    g = _bn_g(dy, dy2, row_scale2, gscale)
+    xh, pre = _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn)
+    if use_relu:
+        g = g * (pre > 0)
+    return torch.cat([g.sum(0), (g * xh).sum(0)])
+
+
+def bn_bwd(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale, dres=None,
+           dres_accumulate=False, want_dz_colsum=False, out_row_scale=None):
+    graw = _bn_g(dy, dy2, row_scale2, gscale)
+    if dres is not None:
+        _st(dres, graw + (dres.float() if dres_accumulate else 0.0))
+    xh, pre = _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn)
+    g = graw * (pre > 0) if use_relu else graw
+    sums = None
+    if use_bn and training:
+        sums = torch.cat([g.sum(0), (g * xh).sum(0)])
+        n = z.shape[0]
+        d = gamma * rstd * (g - sums[:z.shape[1]] / n - xh * sums[z.shape[1]:] / n)
+    elif use_bn:
+        d = gamma * rstd * g
+    else:
+        d = g
+    colsum = d.sum(0) if want_dz_colsum else None
+    if out_row_scale is not None:
+        d = d * out_row_scale[:, None]
+    return _st(new_like(z), d), sums, colsum
+
+
+def axpby(x, y, a, b, out_dtype=None, row_scale=None, out=None):
+    v = a * x.float() + (b * y.float() if y is not None else 0.0)
+    if row_scale is not None:
+        v = v * row_scale[:, None]
+    if out is None:
+        out = torch.zeros(x.shape, dtype=out_dtype or x.dtype)
+    return _st(out, v)
+
+
+def head_mean(x, heads, d):
+    return _st(alloc_act(x.shape[0], d, x.dtype, x.device), x.float().reshape(x.shape[0], heads, d).mean(1))
+
+
+def attn_prepare_fwd(s_raw, z_raw, nq2v, nk2v, planes):
+    inq, ink = nq2v.sum().rsqrt(), nk2v.sum().rsqrt()
+    inv = inq * ink
+    m, d = s_raw.shape
+    bm = (s_raw.t() * inv).contiguous()
+    bt = torch.zeros(16, m)
+    bt[0] = z_raw * inv
+    if planes == 1:
+        bm, bt = bm.bfloat16().float(), bt.bfloat16().float()
+    return Operand(bm, d, m, m, planes), Operand(bt, 16, m, m, planes), torch.stack([inq, ink, inv, torch.zeros(())])
+
+
+def attn_bwd_prep(g, o, den, gscale):
+    inv = gscale / den
+    gnum = _st(alloc_act(g.shape[0], g.shape[1], g.dtype, g.device), g.float() * inv[:, None])
+    gden = -(g.float() * o.float()).sum(1) * inv
+    return gnum, gden
+
+
+def attn_prepare_bwd(s_raw, z_raw, ds_raw, dz_raw, scal_fwd, planes, scal_bwd):
+    inq, ink, alpha = scal_fwd[0], scal_fwd[1], scal_fwd[2]
+    c = alpha * ((s_raw * ds_raw).sum() + (z_raw * dz_raw).sum())
+    scal_bwd[0], scal_bwd[1], scal_bwd[2], scal_bwd[3] = alpha, -c * inq * inq, -c * ink * ink, c
+    m, d = s_raw.shape
+
+    def op(t):
+        t = t.contiguous()
+        if planes == 1:
+            t = t.bfloat16().float()
+        return Operand(t, t.shape[0], t.shape[1], t.shape[1], planes)
+
+    return op(s_raw), op(ds_raw.t()), op(ds_raw), alpha * z_raw, alpha * dz_raw
+
+
+def attn_combine_scal(scal_bwd_all, heads, scal_fwd):
+    c = scal_bwd_all[:, 3].sum()
+    scal_bwd_all[:, 1] = -c * scal_fwd[0] ** 2
+    scal_bwd_all[:, 2] = -c * scal_fwd[1] ** 2
+
+
+def launch_count():
+    return 0
+
+
+class EmuGraph:
+    def __init__(self, edge_index, n, self_loop_mode=0):
+        self.n, self.edge_index, self.self_loop_mode = n, edge_index, self_loop_mode
+        self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True)
+
+    def transpose(self):
+        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False)
+        return rp, cl
