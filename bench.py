@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — nodes/sec of one SGFormer training step (fwd + loss + bwd + Adam) on synthetic graphs of the reference's
+shapes (BASELINE.json).  One JSON line on stdout (rank 0).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                       # ogbn-products-shaped, bf16, full batch
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # rank-local graph partitions + grad allreduce
+    python bench.py --impl reference                                     # the reference's CPU path (oracle port) on host cores
+
+Timed region: device-timed with CUDA events on the launching stream, barrier + synchronize on both sides, max over
+ranks.  `value` has the inputs resident in HBM; `e2e` re-copies the step's inputs from pinned host memory every step
+(so it also rebuilds the CSR) and reads the loss back.  `roofline` is the CSR SpMM (the dominant kernel): algorithmic
+bytes per launch / its CUDA-event duration inside the timed steps, against MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# workload -> (N, d_in, E_stored, classes, hidden, gnn layers, use_init, precision)
+WORKLOADS = {
+    "products": dict(n=2449029, d=100, e=61859140, c=47, h=256, layers=3, use_init=True, precision="bf16"),
+    "arxiv": dict(n=169343, d=128, e=1166243, c=40, h=256, layers=3, use_init=False, precision="fp32"),
+    "pokec": dict(n=1632803, d=65, e=30622564, c=2, h=64, layers=2, use_init=True, precision="bf16"),
+    "papers-batch": dict(n=400000, d=128, e=430000, c=172, h=256, layers=3, use_init=True, precision="bf16"),
+    "tiny": dict(n=20000, d=64, e=200000, c=7, h=64, layers=2, use_init=True, precision="bf16"),
+}
+
+
+def model_kwargs(w):
+    # large/run.sh recipes: 1 attention layer (residual, weight, LN; no act), GCN with bn/residual/weight/act
+    return dict(trans_num_layers=1, trans_num_heads=1, trans_dropout=0.0, trans_use_bn=True, trans_use_residual=True,
+                trans_use_weight=True, trans_use_act=False, gnn_num_layers=w["layers"], gnn_dropout=0.0, gnn_use_weight=True,
+                gnn_use_init=w["use_init"], gnn_use_bn=True, gnn_use_residual=True, gnn_use_act=True, use_graph=True,
+                graph_weight=0.5, aggregate="add")
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def spmm_algorithmic_bytes(n, nnz, h, b):
+    """nnz*4 (int32 col) + (n+1)*8 (int64 rowptr) + nnz*h*b (gathered rows) + n*h*b (output)."""
+    return nnz * 4 + (n + 1) * 8 + nnz * h * b + n * h * b
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(w, budget_nodes=60000, repeats=1):
+    from oracle import sgformer_oracle as O
+    from sgformer_b200.synth import make_graph
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    frac = min(1.0, budget_nodes / w["n"])
+    n = max(1000, int(w["n"] * frac))
+    e = max(1000, int(w["e"] * frac))          # same average degree as the full workload
+    kw = model_kwargs(w)
+    cfg = O.make_config("large", w["d"], w["h"], w["c"], **kw)
+    sd = O.init_state_dict(cfg, seed=0)
+    ei = make_graph(n, e, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, w["d"], generator=g)
+    y = torch.randint(0, w["c"], (n,), generator=g)
+
+    def step():
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+               for k, v in sd.items()}
+        out = O.sgformer_forward(cfg, sdg, x, ei, training=True)
+        torch.nn.functional.nll_loss(torch.log_softmax(out, 1), y).backward()
+
+    best = float("inf")
+    for _ in range(max(1, repeats)):
+        t0 = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t0)
+    return dict(value=n / best, unit="nodes/s", cores=threads, kind="port",
+                sample=f"oracle/sgformer_oracle.py (torch-CPU restatement of large/ours.py) train-mode fwd+bwd on a "
+                       f"{n}-node / {ei.shape[1]}-edge subsample with the workload's mean degree, {threads} threads, "
+                       f"best of {max(1, repeats)}", seconds=best, nodes=n)
+
+
+def run_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference(w, budget_nodes=10000)
+    res = None
+    for _ in range(max(1, args.steps)):
+        res = cpu_reference(w, budget_nodes=args.ref_nodes)
+        vals.append(res["seconds"])
+        if time.perf_counter() - t_all > 240:
+            break
+    sec = statistics.mean(vals)
+    value = res["nodes"] / sec
+    line = {"impl": "reference", "metric": "nodes/sec fwd+bwd", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wname, "sample_nodes": res["nodes"], "hidden": w["h"], "gnn_layers": w["layers"]},
+            "cpu_baseline": {k: res[k] for k in ("unit", "cores", "kind", "sample")} | {"value": value},
+            "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SGF_BENCH_WORKLOAD", "products"), choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
+    ap.add_argument("--ref-nodes", type=int, default=60000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.precision:
+        w["precision"] = args.precision
+    if args.impl == "reference":
+        return run_reference(args, w, args.workload)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sgformer_b200 import kernels as K
+    from sgformer_b200 import large as L
+    from sgformer_b200.graph import get_graph
+    from sgformer_b200.synth import make_graph
+
+    torch.manual_seed(1234)
+    n, d, c, h = w["n"], w["d"], w["c"], w["h"]
+    # rank-local graph partition of the named shape (same shape on every rank, different seed): weak scaling
+    ei = make_graph(n, w["e"], seed=100 + rank, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    x = torch.randn(n, d, generator=g, device=dev)
+    y = torch.randint(0, c, (n,), generator=g, device=dev)
+    model = L.SGFormer(d, h, c, **model_kwargs(w)).to(dev).set_precision(w["precision"])
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    opt = torch.optim.Adam([{"params": model.params1, "weight_decay": 0.0}, {"params": model.params2, "weight_decay": 0.0}],
+                           lr=1e-3, fused=True)
+    model.train()
+    params = [p for p in model.parameters()]
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        o = 0
+        for p in params:
+            if p.grad is not None:
+                k = p.grad.numel()
+                p.grad.copy_(flat[o:o + k].view_as(p.grad))
+                o += k
+
+    def step(xd, eid, yd):
+        opt.zero_grad(set_to_none=True)
+        out = model(xd, eid)
+        loss = torch.nn.functional.nll_loss(torch.log_softmax(out, dim=1), yd)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    for _ in range(args.warmup):
+        step(x, ei, y)
+    graph = get_graph(ei, n, 0)
+    nnz = graph.nnz
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    K.spmm_events = []
+    l0 = K.launch_count()
+    ms_step = timed(lambda: step(x, ei, y), args.steps)
+    launches = K.launch_count() - l0
+    ev = K.spmm_events
+    K.spmm_events = None
+    clocks = sampler.stop() if sampler else None
+    spmm_ms = [a.elapsed_time(b) for a, b in ev]
+    value = n * world / (ms_step * 1e-3)
+
+    # end to end: inputs come from pinned host memory every step, loss is read back
+    e2e = None
+    if not args.no_e2e:
+        xh, eih, yh = x.cpu().pin_memory(), ei.cpu().pin_memory(), y.cpu().pin_memory()
+        h2d = xh.numel() * xh.element_size() + eih.numel() * eih.element_size() + yh.numel() * yh.element_size()
+
+        def e2e_step():
+            loss = step(xh.to(dev, non_blocking=True), eih.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+            return loss.item()
+
+        e2e_step()
+        ms_e2e = timed(e2e_step, max(2, min(args.steps, 5)))
+        e2e = {"value": n * world / (ms_e2e * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    b = 2 if w["precision"] == "bf16" else 4
+    alg = spmm_algorithmic_bytes(n, nnz, h, b)
+    peak, peak_src = peaks()
+    roof = None
+    if spmm_ms:
+        avg_ms = statistics.mean(spmm_ms)
+        achieved = alg / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        roof = {"kernel": "spmm_rows_kernel (CSR SpMM fwd + transposed bwd)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_timed": len(spmm_ms),
+                "share_of_step": sum(spmm_ms) / (ms_step * args.steps), "frac_of_nominal_8TBs": achieved / 8000.0}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference(w, budget_nodes=args.ref_nodes)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": "nodes/sec fwd+bwd", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": w["precision"], "data": "synthetic",
+            "config": {"workload": f"ogbn-{args.workload}-shaped synthetic, full batch" if args.workload != "papers-batch"
+                       else "papers100M-shaped mini-batch (400k nodes)", "nodes_per_gpu": n, "nnz_per_gpu": nnz,
+                       "in_features": d, "hidden": h, "classes": c, "gnn_layers": w["layers"], "gnn_use_init": w["use_init"],
+                       "attn_layers": 1, "parallelism": "single GPU" if world == 1 else
+                       f"dp{world}: rank-local graph partitions, replicated model, NCCL grad allreduce",
+                       "step": "zero_grad + forward + log_softmax/NLL + backward + fused Adam",
+                       "l2": "inputs (>= 1 GB of activations per pass) exceed the 126 MB L2; no explicit flush"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,10 @@ def subgraph(edge_index: Tensor, n: int, subset: Tensor) -> Tensor:
     return out[:, :k]
 
 
+# bench.py sets this to a list to collect (start, end) CUDA events around every SpMM launch (roofline measurement)
+spmm_events = None
+
+
 def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     _use(x)
     n = rowptr.numel() - 1
@@ -139,8 +143,15 @@ def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, ou
     _, ho, ldy = _mat(out, "out")
     if ho != h or out.dtype != x.dtype:
         raise ValueError("spmm: out shape/dtype mismatch")
+    ev = spmm_events
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().sgf_spmm(_p(rowptr), _p(col), _p(_f32vec(row_scale, n, "row_scale")), _p(x), ldx, _p(out), ldy, n, h,
                          dcode(x), _stream()), "sgf_spmm")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
     return out
 
 

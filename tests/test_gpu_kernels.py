@@ -1,0 +1,388 @@
+"""Kernel-level parity on the B200: every C-ABI kernel against the oracle / its documented semantics.
+
+Integer work (CSR build, subgraph) is compared bit-exactly with the numpy / C oracle; floating-point kernels against
+fp64 numpy (SpMM, attention contractions) or the torch-CPU statement of the kernel contract (tests/kernel_emu.py,
+itself pinned to the reference through tests/test_schedule_emulated.py)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kernel_emu as emu
+from oracle import np_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def K():
+    from sgformer_b200 import kernels
+    return kernels
+
+
+def rand_graph(n, e, seed, directed=False, isolated=0, dup=0, hub=0):
+    g = torch.Generator().manual_seed(seed)
+    hi = max(n - isolated, 1)
+    src = torch.randint(0, hi, (e,), generator=g)
+    dst = torch.randint(0, hi, (e,), generator=g)
+    if hub:
+        dst[:hub] = 3 % hi  # one node with a huge in-degree
+    ei = torch.stack([src, dst])
+    if not directed:
+        ei = torch.cat([ei, ei.flip(0)], 1)
+    if dup:
+        ei = torch.cat([ei, ei[:, :dup]], 1)
+    return ei[:, torch.randperm(ei.shape[1], generator=g)].contiguous()
+
+
+def _close(a, b, rtol, atol, what):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    ref = b.abs().max().item() if b.numel() else 0.0
+    assert np.isfinite(err) and err <= atol + rtol * ref, f"{what}: max err {err:.3e} (ref max {ref:.3e})"
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K9: integers, bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [
+    dict(n=1, e=0), dict(n=7, e=0), dict(n=50, e=200), dict(n=300, e=3000, directed=True, isolated=11, dup=57),
+    dict(n=2000, e=60000), dict(n=500, e=9000, directed=True, hub=3000), dict(n=1000, e=300, directed=True, hub=280),
+    dict(n=40000, e=400000),
+])
+@pytest.mark.parametrize("by_source", [False, True])
+def test_csr_build_bit_exact(K, case, by_source):
+    c = dict(case)
+    n, e = c.pop("n"), c.pop("e")
+    ei = rand_graph(n, e, 1, **c) if e else torch.zeros((2, 0), dtype=torch.int64)
+    rowptr, col, dinv = K.csr_build(ei.to(DEV), n, by_source, 0, True)
+    eio = ei.flip(0) if by_source else ei
+    rp, cl, dv = np_ref.gcn_csr(eio.numpy(), n)
+    assert np.array_equal(rowptr.cpu().numpy(), rp), "rowptr differs"
+    assert np.array_equal(col.cpu().numpy(), cl), "col differs"
+    if not by_source:
+        assert np.array_equal(dinv.cpu().numpy(), dv), "dinv differs (bitwise)"
+
+
+def test_csr_build_matches_c_oracle(K):
+    """The C restatement (oracle/csr_ref.c, built by __graft_entry__.build) against the CUDA build."""
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_build", "libcsr_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_build/libcsr_ref.so not built")
+    lib = ctypes.CDLL(so)
+    n = 777
+    ei = rand_graph(n, 5000, 9, directed=True, dup=100, isolated=5)
+    nnz = ei.shape[1]
+    rp = np.zeros(n + 1, dtype=np.int64)
+    cl = np.zeros(nnz, dtype=np.int32)
+    ein = np.ascontiguousarray(ei.numpy())
+    rc = lib.sgf_oracle_csr_build(ein.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(nnz), ctypes.c_int64(n), 0,
+                                  rp.ctypes.data_as(ctypes.c_void_p), cl.ctypes.data_as(ctypes.c_void_p), None)
+    assert rc == 0
+    rowptr, col, _ = K.csr_build(ei.to(DEV), n)
+    assert np.array_equal(rowptr.cpu().numpy(), rp) and np.array_equal(col.cpu().numpy(), cl)
+
+
+def test_csr_build_pyg_self_loops(K):
+    n = 400
+    ei = rand_graph(n, 3000, 4, directed=True, dup=30)
+    ei[1, :20] = ei[0, :20]  # some explicit self loops
+    rowptr, col, dinv = K.csr_build(ei.to(DEV), n, False, 1, True)
+    rp, cl, dv = emu.csr_build(ei, n, False, 1, True)
+    assert torch.equal(rowptr.cpu(), rp) and torch.equal(col.cpu(), cl)
+    _close(dinv, dv, 1e-7, 0, "dinv")
+
+
+def test_subgraph_bit_exact(K):
+    n = 5000
+    ei = rand_graph(n, 40000, 2)
+    g = torch.Generator().manual_seed(0)
+    subset = torch.randperm(n, generator=g)[:1500]
+    out = K.subgraph(ei.to(DEV), n, subset.to(DEV))
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[subset] = True
+    keep = mask[ei[0]] & mask[ei[1]]
+    relabel = torch.zeros(n, dtype=torch.long)
+    relabel[subset] = torch.arange(subset.numel())
+    assert torch.equal(out.cpu(), relabel[ei[:, keep]])
+    empty = K.subgraph(ei.to(DEV), n, torch.zeros(0, dtype=torch.long, device=DEV))
+    assert empty.shape == (2, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K6/K7: SpMM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,h", [(torch.float32, 4), (torch.float32, 64), (torch.float32, 100), (torch.float32, 256),
+                                     (torch.bfloat16, 8), (torch.bfloat16, 64), (torch.bfloat16, 96),
+                                     (torch.bfloat16, 128), (torch.bfloat16, 256), (torch.bfloat16, 512)])
+def test_spmm_matches_scipy(K, dtype, h):
+    n = 3000
+    ei = rand_graph(n, 40000, 5, directed=True, dup=200, isolated=17, hub=700)
+    rowptr, col, dinv = K.csr_build(ei.to(DEV), n)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, h, generator=g)
+    xd = x.to(DEV).to(dtype)
+    xs = K.axpby(xd, None, 1.0, 0.0, row_scale=dinv)
+    y = K.spmm(rowptr, col, dinv, xs)
+    ref = np_ref.spmm_fp64(ei.numpy(), n, xd.float().cpu().numpy())
+    tol = 1e-5 if dtype == torch.float32 else 1.5e-2
+    _close(y.float(), ref, tol, tol * 1e-2, f"spmm {dtype} h={h}")
+    # linearity (size-independent property): A(x + 2x') = Ax + 2Ax'
+    if dtype == torch.float32:
+        x2 = torch.randn(n, h, generator=g).to(DEV)
+        lhs = K.spmm(rowptr, col, None, K.axpby(xd, x2, 1.0, 2.0))
+        rhs = K.axpby(K.spmm(rowptr, col, None, xd), K.spmm(rowptr, col, None, x2), 1.0, 2.0)
+        _close(lhs, rhs, 1e-5, 1e-5, "spmm linearity")
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels vs the kernel contract
+# ------------------------------------------------------------------------------------------------
+def _acts(n, h, dtype, seed, k=1):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(n, h, generator=g).to(dtype) for _ in range(k)]
+
+
+@pytest.mark.parametrize("dtype,h,n", [(torch.float32, 32, 1000), (torch.bfloat16, 64, 777), (torch.bfloat16, 256, 2500),
+                                       (torch.float32, 256, 300), (torch.bfloat16, 16, 5), (torch.bfloat16, 96, 1234)])
+def test_row_kernels(K, dtype, h, n):
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    x, r, dy, z, res, mix = _acts(n, h, dtype, 3, 6)
+    g = torch.Generator().manual_seed(8)
+    gamma, beta, zb = 1 + 0.1 * torch.randn(h, generator=g), 0.1 * torch.randn(h, generator=g), 0.2 * torch.randn(h, generator=g)
+    w = torch.rand(n, generator=g)
+    D = lambda t: None if t is None else t.to(DEV)
+
+    s, q = K.colstats(D(x), D(w))
+    se, qe = emu.colstats(x, w)
+    _close(s, se, tol, tol * n ** 0.5, "colstats sum")
+    _close(q, qe, tol, tol, "colstats sumsq")
+
+    for use_ln, use_relu, rr in [(True, True, r), (True, False, None), (False, True, r)]:
+        y, st = K.ln_fwd(D(x), D(rr), 0.7, 0.3, D(gamma), D(beta), use_ln, use_relu, 0.0, 1)
+        ye, ste = emu.ln_fwd(x, rr, 0.7, 0.3, gamma, beta, use_ln, use_relu, 0.0, 1)
+        _close(y.float(), ye.float(), tol, tol, f"ln_fwd ln={use_ln}")
+        if use_ln:
+            _close(st, ste, 1e-4, 1e-5, "ln stats")
+        dg, db = torch.zeros(h, device=DEV), torch.zeros(h, device=DEV)
+        dge, dbe = torch.zeros(h), torch.zeros(h)
+        dx, dr = K.ln_bwd(D(dy), D(x), D(rr), 0.7, 0.3, D(gamma), D(beta), st, use_ln, use_relu, 0.0, 1, 0.5, rr is not None, dg, db)
+        dxe, dre = emu.ln_bwd(dy, x, rr, 0.7, 0.3, gamma, beta, ste, use_ln, use_relu, 0.0, 1, 0.5, rr is not None, dge, dbe)
+        _close(dx.float(), dxe.float(), tol, tol, "ln_bwd dx")
+        if rr is not None:
+            _close(dr.float(), dre.float(), tol, tol, "ln_bwd dr")
+        if use_ln:
+            _close(dg, dge, tol, tol * n ** 0.5, "ln dgamma")
+            _close(db, dbe, tol, tol * n ** 0.5, "ln dbeta")
+
+    rs = torch.rand(n, generator=g) + 0.5
+    for use_bn, use_relu, training in [(True, True, True), (True, False, False), (False, True, True)]:
+        rm, rv = 0.1 * torch.randn(h, generator=g), 1 + 0.2 * torch.rand(h, generator=g)
+        rmd, rvd = D(rm.clone()), D(rv.clone())
+        if use_bn and training:
+            s, q = K.colstats(D(z))
+            mean, rstd = K.bn_finalize(s, q, n, h, D(zb), rmd, rvd, DEV)
+            se, qe = emu.colstats(z)
+            me, re_ = emu.bn_finalize(se, qe, n, h, zb, rm, rv, "cpu")
+            _close(rmd, rm, 1e-4, 1e-5, "running mean")
+            _close(rvd, rv, 1e-3, 1e-4, "running var")
+        elif use_bn:
+            mean, rstd = K.bn_finalize(None, None, n, h, None, rmd, rvd, DEV)
+            me, re_ = emu.bn_finalize(None, None, n, h, None, rm, rv, "cpu")
+        else:
+            mean = rstd = me = re_ = None
+        if use_bn:
+            _close(mean, me, 1e-3, 1e-4, "bn mean")
+            _close(rstd, re_, 2e-3, 1e-4, "bn rstd")
+            me, re_ = mean.cpu(), rstd.cpu()  # identical statistics downstream
+        y, ys = K.bn_fwd(D(z), D(res), D(mix), mean, rstd, D(gamma), D(beta), D(zb), use_bn, use_relu, 0.0, 1, 0.6, D(rs), True, True)
+        ye, yse = emu.bn_fwd(z, res, mix, me, re_, gamma, beta, zb, use_bn, use_relu, 0.0, 1, 0.6, rs, True, True)
+        _close(y.float(), ye.float(), tol, tol, f"bn_fwd y bn={use_bn}")
+        _close(ys.float(), yse.float(), tol, tol, "bn_fwd y_scaled")
+        dres = D(res.clone())
+        dz, sums, cs = K.bn_bwd(D(dy), D(x), D(rs), D(z), mean, rstd, D(gamma), D(beta), D(zb), use_bn, use_relu, training, 0.0, 1,
+                                0.8, dres=dres, dres_accumulate=True, want_dz_colsum=True, out_row_scale=D(rs))
+        drese = res.clone()
+        dze, sumse, cse = emu.bn_bwd(dy, x, rs, z, me, re_, gamma, beta, zb, use_bn, use_relu, training, 0.0, 1, 0.8, dres=drese,
+                                     dres_accumulate=True, want_dz_colsum=True, out_row_scale=rs)
+        _close(dz.float(), dze.float(), tol, tol, f"bn_bwd dz bn={use_bn} train={training}")
+        _close(dres.float(), drese.float(), tol, tol, "bn_bwd dres")
+        _close(cs, cse, tol, tol * n ** 0.5, "bn_bwd dz colsum")
+        if sums is not None:
+            _close(sums, sumse, tol, tol * n ** 0.5, "bn_bwd sums")
+
+    out = K.axpby(D(x), D(r), 0.25, -1.5, out_dtype=torch.float32, row_scale=D(rs))
+    _close(out, emu.axpby(x, r, 0.25, -1.5, torch.float32, rs), tol, tol, "axpby")
+    if h % 4 == 0:
+        _close(K.head_mean(D(x), 4, h // 4).float(), emu.head_mean(x, 4, h // 4).float(), tol, tol, "head_mean")
+    den = torch.rand(n, generator=g) + 1.0
+    gnum, gden = K.attn_bwd_prep(D(dy), D(x), D(den), 0.5)
+    gne, gde = emu.attn_bwd_prep(dy, x, den, 0.5)
+    _close(gnum.float(), gne.float(), tol, tol, "attn_bwd_prep gnum")
+    _close(gden, gde, tol, tol, "attn_bwd_prep gden")
+
+
+def test_dropout_statistics_and_consistency(K):
+    """Dropout cannot match torch's Philox stream: check rate, scaling and fwd/bwd mask agreement."""
+    n, h, p = 4096, 128, 0.3
+    x = torch.ones(n, h, device=DEV)
+    y, _ = K.ln_fwd(x, None, 1.0, 0.0, None, None, False, False, p, 1234)
+    kept = (y > 0).float().mean().item()
+    assert abs(kept - (1 - p)) < 0.01
+    _close(y[y > 0], torch.full_like(y[y > 0], 1 / (1 - p)), 1e-6, 0, "dropout scale")
+    dx, _ = K.ln_bwd(x, x, None, 1.0, 0.0, None, None, None, False, False, p, 1234, 1.0, False, None, None)
+    assert torch.equal(dx > 0, y > 0), "forward / backward masks differ"
+    y2, _ = K.ln_fwd(x, None, 1.0, 0.0, None, None, False, False, p, 1235)
+    assert not torch.equal(y2 > 0, y > 0)
+    z = torch.ones(n, h, device=DEV)
+    yb, _ = K.bn_fwd(z, None, None, None, None, None, None, None, False, False, p, 77, 1.0, None, True, False)
+    dz, _, _ = K.bn_bwd(z, None, None, z, None, None, None, None, None, False, False, True, p, 77, 1.0)
+    assert abs((yb > 0).float().mean().item() - (1 - p)) < 0.01 and torch.equal(dz > 0, yb > 0)
+
+
+def test_pack_operand(K):
+    g = torch.Generator().manual_seed(2)
+    src = torch.randn(130, 47, generator=g)
+    for transpose in (False, True):
+        for planes in (1, 3):
+            cs = torch.zeros(47, device=DEV)
+            op = K.pack_operand(src.to(DEV), transpose, planes, colsum=cs)
+            want = src.t() if transpose else src
+            data = op.data.float().cpu()
+            rec = sum(data[:, i * op.kp:i * op.kp + op.k] for i in range(planes))
+            _close(rec, want, 1e-6 if planes == 3 else 8e-3, 1e-7 if planes == 3 else 1e-3, f"pack t={transpose} p={planes}")
+            assert torch.count_nonzero(data[:, op.k:op.kp]) == 0, "K padding must be zero"
+            _close(cs, src.sum(0), 1e-5, 1e-5, "pack colsum")
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMMs
+# ------------------------------------------------------------------------------------------------
+def _ops(K, a, b, planes):
+    """CUDA + emulated operands for fp32 sources a [rows,k], b [n,k]."""
+    return (K.pack_operand(a.to(DEV), False, planes), K.pack_operand(b.to(DEV), False, planes),
+            emu.pack_operand(a, False, planes), emu.pack_operand(b, False, planes))
+
+
+@pytest.mark.parametrize("rows,k,n_out", [(1, 16, 16), (127, 64, 32), (128, 100, 47), (1000, 256, 256), (300, 256, 768),
+                                          (5000, 128, 64), (129, 1433, 64), (2000, 64, 172)])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_gemm_nt_affine(K, rows, k, n_out, planes):
+    g = torch.Generator().manual_seed(rows + k)
+    a, b = torch.randn(rows, k, generator=g), torch.randn(n_out, k, generator=g) / k ** 0.5
+    bias, aux = torch.randn(n_out, generator=g), torch.randn(rows, n_out, generator=g)
+    rs, r1r, r1c = torch.rand(rows, generator=g), torch.randn(rows, generator=g), torch.randn(n_out, generator=g)
+    ad, bd = torch.tensor([0.5]), torch.tensor([-2.0])
+    A, B, Ae, Be = _ops(K, a, b, planes)
+    tol = 2e-5 if planes == 3 else 1e-2
+    for out_dtype in (torch.float32, torch.bfloat16):
+        if out_dtype == torch.bfloat16 and n_out % 8:
+            continue
+        out = K.alloc_act(rows, n_out, out_dtype, DEV)
+        K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, out)
+        oe = emu.gemm_nt([Ae], [Be], [(0, 0, 0, 0, k)], n_out, torch.zeros(rows, n_out))
+        t = tol if out_dtype == torch.float32 else max(tol, 1e-2)
+        _close(out.float(), oe, t, t, f"plain {out_dtype}")
+    out = torch.full((rows, n_out), 0.25, device=DEV)
+    K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, out, bias=bias.to(DEV), aux=aux.to(DEV), row_scale=rs.to(DEV), alpha=1.5,
+              beta=0.5, alpha_dev=ad.to(DEV), beta_dev=bd.to(DEV), relu=True, accumulate=True, r1_row=r1r.to(DEV), r1_col=r1c.to(DEV))
+    oe = emu.gemm_nt([Ae], [Be], [(0, 0, 0, 0, k)], n_out, torch.full((rows, n_out), 0.25), bias=bias, aux=aux, row_scale=rs,
+                     alpha=1.5, beta=0.5, alpha_dev=ad, beta_dev=bd, relu=True, accumulate=True, r1_row=r1r, r1_col=r1c)
+    _close(out, oe, tol, tol, "full epilogue")
+
+
+@pytest.mark.parametrize("planes", [1, 3])
+@pytest.mark.parametrize("h", [16, 32, 64, 256])
+def test_gemm_nt_concat_segments(K, planes, h):
+    """[y || x0] . W^T as two K segments of one B source (GraphConvLayer use_init, large/ours.py:37-38)."""
+    rows = 700
+    g = torch.Generator().manual_seed(h)
+    y, x0, w = torch.randn(rows, h, generator=g), torch.randn(rows, h, generator=g), torch.randn(h, 2 * h, generator=g) / h ** 0.5
+    Y, W, Ye, We = _ops(K, y, w, planes)
+    X0, X0e = K.pack_operand(x0.to(DEV), False, planes), emu.pack_operand(x0, False, planes)
+    out = torch.empty(rows, h, device=DEV)
+    pairs = [(0, 0, 0, 0, h), (1, 0, 0, h, h)]
+    K.gemm_nt([Y, X0], [W], pairs, h, out)
+    oe = emu.gemm_nt([Ye, X0e], [We], pairs, h, torch.zeros(rows, h))
+    tol = 2e-5 if planes == 3 else 1e-2
+    _close(out, oe, tol, tol, "concat segments")
+    _close(out, torch.cat([y, x0], 1) @ w.t(), 5e-5 if planes == 3 else 2e-2, 5e-5 if planes == 3 else 2e-2, "vs fp32 matmul")
+
+
+@pytest.mark.parametrize("rows,m,d", [(64, 16, 16), (1000, 64, 64), (777, 128, 128), (3000, 256, 256), (130, 32, 64)])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_gemm_nt_attention_apply(K, rows, m, d, planes):
+    g = torch.Generator().manual_seed(m)
+    q, v = torch.randn(rows, m, generator=g), torch.randn(rows, d, generator=g)
+    s_raw, z_raw = torch.randn(m, d, generator=g) * 3, torch.randn(m, generator=g) * 3
+    nq2v, nk2v = torch.rand(m, generator=g) * rows, torch.rand(m, generator=g) * rows
+    bmat, btail, scal = K.attn_prepare_fwd(s_raw.to(DEV), z_raw.to(DEV), nq2v.to(DEV), nk2v.to(DEV), planes)
+    bme, bte, sce = emu.attn_prepare_fwd(s_raw, z_raw, nq2v, nk2v, planes)
+    _close(scal[:3], sce[:3], 1e-5, 0, "scal")
+    Q, Qe = K.pack_operand(q.to(DEV), False, planes), emu.pack_operand(q, False, planes)
+    out, den = torch.empty(rows, d, device=DEV), torch.empty(rows, device=DEV)
+    K.gemm_nt([Q], [bmat], [(0, 0, 0, 0, m)], d, out, epi=1, aux=v.to(DEV), tail=btail, nf=float(rows), den_out=den)
+    oe, de = torch.zeros(rows, d), torch.zeros(rows)
+    emu.gemm_nt([Qe], [bme], [(0, 0, 0, 0, m)], d, oe, epi=1, aux=v, tail=bte, nf=float(rows), den_out=de)
+    tol = 2e-5 if planes == 3 else 2e-3
+    _close(den, de, tol, tol, "den")
+    _close(out, oe, tol, tol, "attention apply")
+
+
+@pytest.mark.parametrize("rows,m,n", [(1, 16, 16), (63, 32, 47), (64, 64, 64), (1000, 128, 128), (20000, 256, 256),
+                                      (5000, 256, 100), (4097, 47, 256), (300, 768, 256), (300, 64, 1433)])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_gemm_tn(K, rows, m, n, planes):
+    g = torch.Generator().manual_seed(rows + m)
+    a, b = torch.randn(rows, m, generator=g), torch.randn(rows, n, generator=g)
+    A, B = K.pack_operand(a.to(DEV), False, planes), K.pack_operand(b.to(DEV), False, planes)
+    Ae, Be = emu.pack_operand(a, False, planes), emu.pack_operand(b, False, planes)
+    tol = 2e-5 if planes == 3 else 1e-2
+    out = torch.empty(m, n, device=DEV)
+    K.gemm_tn(A, B, out)
+    _close(out, emu.gemm_tn(Ae, Be, torch.zeros(m, n)), tol, tol * rows ** 0.5, "tn")
+    outt = torch.full((n, m), 2.0, device=DEV)
+    K.gemm_tn(A, B, outt, transpose_out=True, alpha=0.5, beta=-1.0, alpha_dev=torch.tensor([3.0], device=DEV))
+    oe = emu.gemm_tn(Ae, Be, torch.full((n, m), 2.0), transpose_out=True, alpha=0.5, beta=-1.0, alpha_dev=torch.tensor([3.0]))
+    _close(outt, oe, tol, tol * rows ** 0.5, "tn transposed/scaled")
+    # determinism of the two-stage reduction
+    out2 = torch.empty(m, n, device=DEV)
+    K.gemm_tn(A, B, out2)
+    assert torch.equal(out, out2), "gemm_tn must be run-to-run deterministic"
+
+
+def test_gemm_on_bf16_views(K):
+    """Operands that are column slices of a wider activation buffer (q/k/v inside the fused qkv buffer)."""
+    g = torch.Generator().manual_seed(0)
+    rows, h = 900, 64
+    qkv = torch.randn(rows, 3 * h, generator=g).to(torch.bfloat16).to(DEV)
+    k_, v_ = qkv[:, h:2 * h], qkv[:, 2 * h:]
+    out = torch.empty(h, h, device=DEV)
+    K.gemm_tn(K.as_operand(k_, 1), K.as_operand(v_, 1), out)
+    _close(out, k_.float().t() @ v_.float(), 1e-3, 1e-2, "tn on views")
+    w = torch.randn(h, h, generator=g)
+    o2 = torch.empty(rows, h, device=DEV)
+    K.gemm_nt([K.as_operand(k_, 1)], [K.pack_operand(w.to(DEV), False, 1)], [(0, 0, 0, 0, h)], h, o2)
+    _close(o2, k_.float().cpu() @ w.bfloat16().float().t(), 1e-3, 1e-2, "nt on views")
+
+
+def test_attention_partials_vs_fp64(K):
+    """S' = k^T v, z', norms against the fp64 einsum oracle with *relative* tolerances."""
+    from sgformer_b200 import engine as E
+    g = torch.Generator().manual_seed(5)
+    for n, hd, m in [(16, 1, 8), (257, 2, 32), (4000, 1, 256)]:
+        q, k, v = (torch.randn(n, hd * m, generator=g) for _ in range(3))
+        ref = np_ref.attention_fp64(q.reshape(n, hd, m).numpy(), k.reshape(n, hd, m).numpy(), v.reshape(n, hd, m).numpy())
+        tape = E.Tape()
+        o = E.attention_forward(q.to(DEV), k.to(DEV), v.to(DEV), hd, E.FP32, tape)
+        for i in range(hd):
+            _close(tape["s"][i], ref["S"][i], 2e-5, 1e-4, f"S' head {i}")
+        _close(tape["z"].reshape(hd, m), ref["z"], 2e-5, 1e-4, "z'")
+        _close(o.reshape(n, hd, m), ref["out"], 1e-5, 1e-5, "attention out")
+        o_b = E.attention_forward(q.to(DEV).bfloat16(), k.to(DEV).bfloat16(), v.to(DEV).bfloat16(), hd, E.BF16, None)
+        _close(o_b.float().reshape(n, hd, m), ref["out"], 1e-2, 1e-2, "attention out bf16")

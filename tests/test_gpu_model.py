@@ -1,0 +1,217 @@
+"""Module-level parity on the B200: the drop-in nn.Modules against the golden fixtures generated from the unmodified
+reference (tests/make_golden.py) and against the CPU oracle on fresh seeded graphs.
+fp32 precision: 1e-4; bf16 precision: 1e-2 (BASELINE.json north_star)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import sgformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODEL_FILES = sorted(glob.glob(os.path.join(GOLD, "model_*.pt")))
+
+
+def _close(a, b, rtol, atol, what):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err == err and err <= atol + rtol * ref, f"{what}: max err {err:.3e} (ref max {ref:.3e})"
+
+
+class Data:
+    def __init__(self, x, ei):
+        self.graph = {"node_feat": x, "edge_index": ei, "num_nodes": x.shape[0]}
+
+
+def build_model(cfg):
+    """Instantiate our drop-in module for an oracle config (same constructor calls as the reference's parse.py)."""
+    v = cfg["variant"]
+    if v == "medium":
+        from sgformer_b200 import medium as M
+        gnn = M.GCN(cfg["in_channels"], cfg["hidden"], cfg["hidden"], num_layers=cfg["gcn_num_layers"],
+                    dropout=cfg["gcn_dropout"], use_bn=cfg["gcn_use_bn"])
+        return M.SGFormer(cfg["in_channels"], cfg["hidden"], cfg["out_channels"], num_layers=cfg["trans_num_layers"],
+                          num_heads=cfg["num_heads"], alpha=cfg["alpha"], dropout=cfg["trans_dropout"],
+                          use_bn=cfg["trans_use_bn"], use_residual=cfg["trans_use_residual"],
+                          use_weight=cfg["trans_use_weight"], use_graph=cfg["use_graph"], graph_weight=cfg["graph_weight"],
+                          gnn=gnn, aggregate=cfg["aggregate"])
+    kw = dict(trans_num_layers=cfg["trans_num_layers"], trans_num_heads=cfg["num_heads"], trans_dropout=cfg["trans_dropout"],
+              trans_use_bn=cfg["trans_use_bn"], trans_use_residual=cfg["trans_use_residual"],
+              trans_use_weight=cfg["trans_use_weight"], trans_use_act=cfg["trans_use_act"],
+              gnn_num_layers=cfg["gnn_num_layers"], gnn_dropout=cfg["gnn_dropout"], gnn_use_weight=cfg["gnn_use_weight"],
+              gnn_use_init=cfg["gnn_use_init"], gnn_use_bn=cfg["gnn_use_bn"], gnn_use_residual=cfg["gnn_use_residual"],
+              gnn_use_act=cfg["gnn_use_act"], use_graph=cfg["use_graph"], graph_weight=cfg["graph_weight"],
+              aggregate=cfg["aggregate"])
+    if v == "100M":
+        from sgformer_b200 import hundred_m as H
+        return H.SGFormer(cfg["in_channels"], cfg["hidden"], cfg["out_channels"], alpha=cfg["alpha"], **kw)
+    from sgformer_b200 import large as L
+    return L.SGFormer(cfg["in_channels"], cfg["hidden"], cfg["out_channels"], **kw)
+
+
+def run(model, cfg, x, ei):
+    return model(Data(x, ei)) if cfg["variant"] == "medium" else model(x, ei)
+
+
+@pytest.mark.parametrize("path", MODEL_FILES, ids=[os.path.basename(p)[6:-3] for p in MODEL_FILES])
+def test_state_dict_keys_match_reference(path):
+    fx = torch.load(path, weights_only=False)
+    model = build_model(fx["cfg"])
+    assert list(model.state_dict().keys()) == list(fx["state_dict"].keys())
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(fx["state_dict"][k].shape), k
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("path", MODEL_FILES, ids=[os.path.basename(p)[6:-3] for p in MODEL_FILES])
+def test_model_matches_reference_golden(path, precision, rtol):
+    fx = torch.load(path, weights_only=False)
+    cfg = fx["cfg"]
+    model = build_model(cfg).to(DEV).set_precision(precision)
+    model.load_state_dict(fx["state_dict"])
+    x, ei = fx["x"].to(DEV), fx["edge_index"].to(DEV)
+    model.eval()
+    with torch.no_grad():
+        out = run(model, cfg, x, ei)
+    assert out.dtype == torch.float32 and out.shape == fx["out_eval"].shape
+    _close(out, fx["out_eval"], rtol, rtol, "eval output")
+
+    model.train()
+    xg = x.clone().requires_grad_(True)
+    out = run(model, cfg, xg, ei)
+    _close(out, fx["out_train"], rtol, rtol, "train output")
+    (out * fx["loss_weight"].to(DEV)).sum().backward()
+    grtol = 2e-3 if precision == "fp32" else 6e-2
+    _close(xg.grad, fx["grad_x"], grtol, grtol * 1e-2, "grad x")
+    got = dict(model.named_parameters())
+    for k, g in fx["grads"].items():
+        assert got[k].grad is not None, f"missing grad {k}"
+        scale = max(g.abs().max().item(), 1e-3)
+        _close(got[k].grad, g, grtol, grtol * scale * 0.05 + 3e-5, f"grad {k}")
+    if precision == "fp32":
+        sd = model.state_dict()
+        for k, v in fx["buffers_after_train"].items():
+            _close(sd[k].float(), v.float(), 1e-4, 1e-5, f"buffer {k}")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_full_attention_conv_golden(precision, tol):
+    from sgformer_b200.medium import full_attention_conv
+    fx = torch.load(os.path.join(GOLD, "attention.pt"), weights_only=False)
+    for name, c in fx.items():
+        q, k, v = (c[t].to(DEV).requires_grad_(True) for t in "qkv")
+        o = full_attention_conv(q, k, v, precision=precision)
+        _close(o, c["out"], tol, tol, f"{name} out")
+        (o * c["w"].to(DEV)).sum().backward()
+        gt = 2e-3 if precision == "fp32" else 8e-2
+        for t, g in (("dq", q.grad), ("dk", k.grad), ("dv", v.grad)):
+            _close(g, c[t], gt, gt * c[t].abs().max().item() * 0.05 + 1e-7, f"{name} {t}")
+    o, att = full_attention_conv(q, k, v, output_attn=True, precision=precision)
+    assert att.shape == (q.shape[0], q.shape[0])
+
+
+def test_graphconv_layer_golden():
+    from sgformer_b200.large import GraphConvLayer
+    fx = torch.load(os.path.join(GOLD, "graphconv_layer.pt"), weights_only=False)
+    for name, c in fx.items():
+        h = c["x"].shape[1]
+        layer = GraphConvLayer(h, h, use_weight=c["use_weight"], use_init=c["use_init"]).to(DEV)
+        with torch.no_grad():
+            layer.W.weight.copy_(c["W"])
+            layer.W.bias.copy_(c["b"])
+        x, x0 = c["x"].to(DEV).requires_grad_(True), c["x0"].to(DEV).requires_grad_(True)
+        y = layer(x, c["edge_index"].to(DEV), x0)
+        _close(y, c["y"], 1e-4, 1e-5, f"{name} y")
+        (y * c["w"].to(DEV)).sum().backward()
+        _close(x.grad, c["dx"], 1e-3, 1e-5, f"{name} dx")
+        if c["dx0"] is not None:
+            _close(x0.grad, c["dx0"], 1e-3, 1e-5, f"{name} dx0")
+        if c["dW"] is not None:
+            _close(layer.W.weight.grad, c["dW"], 1e-3, 1e-4, f"{name} dW")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("n,e,d,h,c,kw", [
+    (20000, 150000, 128, 256, 40, dict(gnn_num_layers=3, graph_weight=0.5)),                       # arxiv recipe, large/run.sh:2-5
+    (30000, 400000, 100, 256, 47, dict(gnn_num_layers=3, gnn_use_init=True, graph_weight=0.5)),    # amazon2m recipe, :15-19
+    (25000, 300000, 65, 64, 2, dict(gnn_num_layers=2, gnn_use_init=True, graph_weight=0.5)),       # pokec recipe, :22-26
+])
+def test_model_matches_oracle_midsize(n, e, d, h, c, kw, precision, tol):
+    """Fresh seeded graph, reference hyper-parameters, sizes the CPU oracle finishes in seconds."""
+    from sgformer_b200.synth import make_graph
+    from sgformer_b200 import large as L
+    cfg = O.make_config("large", d, h, c, gnn_dropout=0.0, trans_dropout=0.0, trans_use_act=False, **kw)
+    sd = O.init_state_dict(cfg, seed=3)
+    ei = make_graph(n, e, seed=1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, d, generator=g)
+    ref = O.sgformer_forward(cfg, sd, x, ei, training=False)
+    model = L.SGFormer(d, h, c, trans_dropout=0.0, gnn_dropout=0.0, trans_use_act=False, **kw).to(DEV).set_precision(precision)
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        out = model(x.to(DEV), ei.to(DEV))
+    _close(out, ref, tol, tol, "eval logits")
+    # train-mode forward (batch statistics) + a loss value
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    y = torch.randint(0, c, (n,), generator=g)
+    ref_t = O.sgformer_forward(cfg, sdg, x, ei, training=True)
+    loss_ref = torch.nn.functional.cross_entropy(ref_t, y)
+    loss_ref.backward()
+    model.train()
+    out_t = model(x.to(DEV), ei.to(DEV))
+    loss = torch.nn.functional.cross_entropy(out_t, y.to(DEV))
+    loss.backward()
+    _close(out_t, ref_t, tol, tol, "train logits")
+    _close(loss, loss_ref, tol, tol, "loss")
+    gt = 5e-3 if precision == "fp32" else 1e-1
+    for k, p in model.named_parameters():
+        gref = sdg[k].grad
+        _close(p.grad, gref, gt, gt * gref.abs().max().item() * 0.05 + 1e-7, f"grad {k}")
+
+
+def test_host_resident_call_runs_on_gpu():
+    """large/eval.py:35-65 `evaluate_large(device='cpu')` moves the model and data to the CPU and calls forward: the
+    drop-in computes on the GPU and returns the logits on the host."""
+    from sgformer_b200 import large as L
+    from sgformer_b200.synth import make_graph
+    model = L.SGFormer(16, 32, 5, gnn_num_layers=2).to(DEV)
+    x, ei = torch.randn(500, 16), make_graph(500, 2000, seed=0)
+    model.eval()
+    with torch.no_grad():
+        ref = model(x.to(DEV), ei.to(DEV)).cpu()
+        model.to("cpu")
+        out = model(x, ei)
+    assert out.device.type == "cpu"
+    _close(out, ref, 1e-6, 1e-6, "host call")
+
+
+def test_reference_plumbing_methods():
+    import copy
+    from sgformer_b200 import large as L
+    model = L.SGFormer(16, 32, 5, gnn_num_layers=2, gnn_use_init=True)
+    assert len(model.params1) + len(model.params2) == len(list(model.parameters()))
+    fc0 = model.fc.weight.clone()
+    model.reset_parameters()
+    assert torch.equal(fc0, model.fc.weight), "reset_parameters must not touch fc (large/ours.py:283-286)"
+    m2 = copy.deepcopy(model).to(DEV)
+    opt = torch.optim.Adam([{"params": m2.params1, "weight_decay": 1e-3}, {"params": m2.params2, "weight_decay": 0.0}], lr=0.01)
+    from sgformer_b200.synth import make_graph
+    x, ei = torch.randn(300, 16, device=DEV), make_graph(300, 1000, seed=0).to(DEV)
+    y = torch.randint(0, 5, (300,), device=DEV)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = torch.nn.functional.nll_loss(torch.log_softmax(m2(x, ei), 1), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], f"loss did not decrease: {losses[0]:.4f} -> {losses[-1]:.4f}"
+    with pytest.raises(ValueError):
+        L.SGFormer(16, 32, 5, aggregate="sum")
+    assert model.get_attentions is not None and print(model) is None
