@@ -54,8 +54,10 @@ def gcn_csr(edge_index, n):
     deg = np.bincount(dst, minlength=n)
     rowptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(deg, out=rowptr[1:])
+    # same operations, in fp32, as the reference: (1. / d).sqrt() with inf -> 0 (large/ours.py:29-32)
     with np.errstate(divide="ignore"):
-        dinv = np.where(deg > 0, 1.0 / np.sqrt(deg.astype(np.float64)), 0.0).astype(np.float32)
+        d32 = deg.astype(np.float32)
+        dinv = np.where(deg > 0, np.sqrt(np.float32(1.0) / d32), np.float32(0.0)).astype(np.float32)
     return rowptr, src[order].astype(np.int32), dinv
 
 

@@ -11,7 +11,7 @@ run() { # name timeout cmd...
   echo "$name rc=$?" >> $OUT/summary.txt
 }
 : > $OUT/summary.txt
-P="python -m pytest -q -x --no-header -p no:cacheprovider"
+P="python -m pytest -q --no-header -p no:cacheprovider"
 run simt 600 $P tests/test_gpu_kernels.py -m gpu -k "csr or subgraph or spmm or row_kernels or dropout or pack"
 run gemm_nt 600 $P tests/test_gpu_kernels.py -m gpu -k "gemm_nt"
 run gemm_tn 600 $P tests/test_gpu_kernels.py -m gpu -k "gemm_tn"
