@@ -172,6 +172,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
         :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// smem tile -> global through the tensor map (rows/cols outside the tensor are clipped by the hardware)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------
@@ -213,6 +229,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100):
@@ -251,10 +281,25 @@ __host__ __device__ __forceinline__ uint32_t hash_u64(uint64_t x) {
     x ^= x >> 33;
     return static_cast<uint32_t>(x >> 11);
 }
-// keep-probability test for element `idx` of the tensor identified by `seed`; returns 0 or 1/(1-p)
-__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
-    uint32_t r = hash_u64(seed * 0x9E3779B97F4A7C15ULL + idx);
-    return ((r & 0xFFFFFFu) * (1.0f / 16777216.0f)) >= p ? inv_keep : 0.0f;
+// Dropout of one 16-byte chunk (VN = 4 or 8 elements): one 64-bit hash per 4 elements, 16 random bits per element.
+// thr16 = round(p * 65536); an element is kept when its 16 bits >= thr16 and scaled by inv_keep = 65536 / (65536 - thr16).
+// The mask is a pure function of (seed, chunk_id) so the backward recomputes it (chunk_id = row * chunks_per_row + chunk).
+template <int VN>
+__device__ __forceinline__ void dropout_chunk(uint64_t seed, uint64_t chunk_id, uint32_t thr16, float inv_keep, float* f) {
+#pragma unroll
+    for (int k = 0; k < VN / 4; ++k) {
+        uint64_t x = seed + (chunk_id * (VN / 4) + k) * 0x9E3779B97F4A7C15ULL;
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+        x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+        x ^= x >> 33;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t u = static_cast<uint32_t>(x >> (16 * j)) & 0xFFFFu;
+            f[4 * k + j] *= (u >= thr16) ? inv_keep : 0.f;
+        }
+    }
 }
+__host__ __device__ __forceinline__ uint32_t dropout_thr16(float p) { return static_cast<uint32_t>(p * 65536.f + 0.5f); }
+__host__ __device__ __forceinline__ float dropout_inv_keep(uint32_t thr16) { return 65536.f / (65536.f - static_cast<float>(thr16)); }
 
 }  // namespace sgf

@@ -40,32 +40,40 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (pitch ld elements), box = [box_rows x 64 cols], 128-byte swizzle, OOB -> 0
-static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D row-major [rows, cols] (pitch ld elements) of bf16 (dtype 1) or fp32 (dtype 0); box = [box_rows x 128 bytes],
+// 128-byte swizzle, OOB loads -> 0, OOB stores clipped
+static int make_tmap_2d(CUtensorMap* tm, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return SGF_ERR_DRIVER;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || rows <= 0 || cols <= 0 || box_rows <= 0 || box_rows > 256)
+    const int es = dtype == 1 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * es) % 16 != 0 || rows <= 0 || cols <= 0 || box_rows <= 0 || box_rows > 256)
         return SGF_ERR_ARG;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SGF_OK : SGF_ERR_DRIVER;
+}
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return make_tmap_2d(tm, base, 1, rows, cols, ld, box_rows);
 }
 
 // ================================================================================================
 // gemm_nt
 // ================================================================================================
 namespace nt {
-constexpr int BM = 128, BK = 64, STAGES = 4, THREADS = 192;
+constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quadrant
+constexpr int THREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES_MAX = (256 + 16) * BK * 2;  // 34 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int STG_BYTES = BM * 128;               // output staging tile: 128 rows x 128 bytes (SW128), 2 per epilogue half
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + BAR_BYTES + 1024;
 
 struct Seg {
     int a_idx, a_koff, b_idx, b_koff, k_blocks;
@@ -86,11 +94,13 @@ struct Params {
     int relu, accumulate;
     float nf; float* den_out;
     const float* r1_row; const float* r1_col;
+    int tma_store;   // 1: epilogue stages 128-byte rows in smem and stores them with TMA; 0: direct global stores
 };
 struct Tmaps {
     CUtensorMap a[SGF_MAX_SRC];
     CUtensorMap b[SGF_MAX_SRC];
     CUtensorMap tail;
+    CUtensorMap out;
 };
 
 __device__ __forceinline__ void load16(const void* base, int dtype, int64_t off, float* f) {
@@ -127,7 +137,8 @@ __device__ __forceinline__ void store1(void* base, int dtype, int64_t off, float
 __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ Tmaps tm, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + 4 * STG_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -144,8 +155,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             tma_prefetch_desc(&tm.b[p.seg[i].b_idx]);
         }
         if (p.has_tail) tma_prefetch_desc(&tm.tail);
+        if (p.tma_store) tma_prefetch_desc(&tm.out);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -215,14 +227,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // ===== epilogue: TMEM -> registers -> (smem staging -> TMA store | direct global stores) =====
+        const int ew = warp - 2;     // 0..7
+        const int q = warp & 3;      // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;    // the two halves alternate over column groups
         float alpha = p.alpha, beta = p.beta;
         if (p.alpha_dev) alpha *= *p.alpha_dev;
         if (p.beta_dev) beta *= *p.beta_dev;
         const int out_es = p.out_dtype == 1 ? 2 : 4, aux_es = p.aux_dtype == 1 ? 2 : 4;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.ldo * out_es) % 16 == 0);
         const bool aux_vec_ok = !p.aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ld_aux * aux_es) % 16 == 0));
+        const bool vecf_ok = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                             (!p.r1_col || (reinterpret_cast<uintptr_t>(p.r1_col) & 15) == 0);
+        const int GW = p.out_dtype == 1 ? 64 : 32;            // columns per 128-byte staging row
+        uint8_t* stg = staging + half * 2 * STG_BYTES;
+        const bool issuer = ((ew & 3) == 0) && lane == 0;    // one TMA-store issuing thread per half
+        const int r_local = q * 32 + lane;
+        uint32_t gcount = 0;
         int64_t it = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = (int)(tile / p.n_blocks), n_blk = (int)(tile % p.n_blocks);
@@ -230,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             const uint32_t acc_phase = (uint32_t)((it / acc_stages) & 1);
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+            const int64_t row = (int64_t)m_blk * BM + r_local;
             const bool row_ok = row < p.rows;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
             const int col_base = n_blk * p.bn_main;
@@ -242,54 +263,115 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                 tmem_ld_wait();
                 const float den = t[0] + p.nf;
                 inv_den = 1.f / den;
-                if (row_ok && p.den_out) p.den_out[row] = den;
+                if (row_ok && p.den_out && half == 0) p.den_out[row] = den;
             }
             const float rs = (p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
             const float r1r = (p.r1_row && row_ok) ? p.r1_row[row] : 0.f;
-            const int n_chunks = p.bn_main / 16;
-            for (int c = 0; c < n_chunks; ++c) {
-                float v[16];
-                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores of the previous chunk
-                tmem_ld16(taddr + c * 16, v);
-                tmem_ld_wait();
-                const int col0 = col_base + c * 16;
-                if (row_ok && col0 < p.n_out) {
-                const bool full16 = col0 + 16 <= p.n_out;
-                float ax[16];
-                if (p.aux) {
-                    if (full16 && aux_vec_ok) load16(p.aux, p.aux_dtype, row * p.ld_aux + col0, ax);
-                    else
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) ax[j] = (col0 + j < p.n_out) ? load1(p.aux, p.aux_dtype, row * p.ld_aux + col0 + j) : 0.f;
+            // -------- 32-column pieces; piece index pc covers tile columns [32*pc, 32*pc+32) --------
+            const int n_pieces = (p.bn_main + 31) / 32;
+            const int ppg = GW / 32;                                   // pieces per staging group (bf16: 2, fp32: 1)
+            const int n_groups = (n_pieces + ppg - 1) / ppg;
+            for (int g = half; g < n_groups; g += 2) {
+                const uint32_t buf = gcount & 1;
+                if (p.tma_store) {
+                    if (issuer) bulk_wait_read<1>();                   // the store that last used this buffer has drained
+                    named_bar_sync(1 + half, 128);
                 }
-                if (p.epi == SGF_EPI_ATTN_APPLY) {
+                for (int pp = 0; pp < ppg; ++pp) {
+                    const int pc = g * ppg + pp;
+                    if (pc >= n_pieces) break;
+                    float v[32];
+                    __syncwarp();  // tcgen05.ld is .sync.aligned
+                    tmem_ld32(taddr + pc * 32, v);
+                    tmem_ld_wait();
+                    const int col0 = col_base + pc * 32;
+                    const int ncol = p.n_out - col0 < 32 ? p.n_out - col0 : 32;   // valid columns of this piece (may be <= 0)
+                    const bool full32 = ncol == 32;
+                    if (row_ok && ncol > 0) {
+                        float ax[32];
+                        if (p.aux) {
+                            if (full32 && aux_vec_ok) { load16(p.aux, p.aux_dtype, row * p.ld_aux + col0, ax); load16(p.aux, p.aux_dtype, row * p.ld_aux + col0 + 16, ax + 16); }
+                            else
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
-                } else {
+                                for (int j = 0; j < 32; ++j) ax[j] = j < ncol ? load1(p.aux, p.aux_dtype, row * p.ld_aux + col0 + j) : 0.f;
+                        }
+                        if (p.epi == SGF_EPI_ATTN_APPLY) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float t = alpha * v[j];
-                        if (p.aux) t += beta * ax[j];
-                        if (p.bias && col0 + j < p.n_out) t += p.bias[col0 + j];
-                        if (p.r1_row && col0 + j < p.n_out) t += r1r * p.r1_col[col0 + j];
-                        if (p.relu) t = fmaxf(t, 0.f);
-                        v[j] = t * rs;
+                            for (int j = 0; j < 32; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+                            if (p.aux)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += beta * ax[j];
+                            if (p.bias) {
+                                if (full32 && vecf_ok && (col0 & 3) == 0) {
+                                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { float4 b4 = __ldg(bp + j); v[4*j] += b4.x; v[4*j+1] += b4.y; v[4*j+2] += b4.z; v[4*j+3] += b4.w; }
+                                } else
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += p.bias[col0 + j];
+                            }
+                            if (p.r1_row) {
+                                if (full32 && vecf_ok && (col0 & 3) == 0) {
+                                    const float4* cp = reinterpret_cast<const float4*>(p.r1_col + col0);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { float4 c4 = __ldg(cp + j); v[4*j] += r1r * c4.x; v[4*j+1] += r1r * c4.y; v[4*j+2] += r1r * c4.z; v[4*j+3] += r1r * c4.w; }
+                                } else
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += r1r * p.r1_col[col0 + j];
+                            }
+                            if (p.relu)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                            if (p.row_scale)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] *= rs;
+                        }
+                        if (p.accumulate) {
+                            float old[32];
+                            if (full32 && vec_ok) { load16(p.out, p.out_dtype, row * p.ldo + col0, old); load16(p.out, p.out_dtype, row * p.ldo + col0 + 16, old + 16); }
+                            else
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) old[j] = j < ncol ? load1(p.out, p.out_dtype, row * p.ldo + col0 + j) : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += old[j];
+                        }
+                        if (!p.tma_store) {
+                            if (full32 && vec_ok) { store16(p.out, p.out_dtype, row * p.ldo + col0, v); store16(p.out, p.out_dtype, row * p.ldo + col0 + 16, v + 16); }
+                            else
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j < ncol) store1(p.out, p.out_dtype, row * p.ldo + col0 + j, v[j]);
+                        }
+                    }
+                    if (p.tma_store) {
+                        // 128-byte staging row, 16-byte chunks XOR-swizzled with (row & 7) (== TMA SWIZZLE_128B); OOB rows/cols
+                        // are clipped by the TMA store, so garbage there is harmless
+                        uint8_t* rowp = stg + buf * STG_BYTES + r_local * 128;
+                        if (p.out_dtype == 1) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int chunk = (pp * 4 + c) ^ (r_local & 7);
+                                *reinterpret_cast<uint4*>(rowp + chunk * 16) = Vec16<__nv_bfloat16>::pack(v + 8 * c);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const int chunk = c ^ (r_local & 7);
+                                *reinterpret_cast<uint4*>(rowp + chunk * 16) = Vec16<float>::pack(v + 4 * c);
+                            }
+                        }
                     }
                 }
-                if (p.accumulate) {
-                    float old[16];
-                    if (full16 && vec_ok) load16(p.out, p.out_dtype, row * p.ldo + col0, old);
-                    else
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) old[j] = (col0 + j < p.n_out) ? load1(p.out, p.out_dtype, row * p.ldo + col0 + j) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += old[j];
-                }
-                if (full16 && vec_ok) store16(p.out, p.out_dtype, row * p.ldo + col0, v);
-                else
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (col0 + j < p.n_out) store1(p.out, p.out_dtype, row * p.ldo + col0 + j, v[j]);
+                if (p.tma_store) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + half, 128);
+                    if (issuer) {
+                        tma_store_2d(&tm.out, stg + buf * STG_BYTES, col_base + g * GW, m_blk * BM);
+                        bulk_commit();
+                    }
+                    ++gcount;
                 }
             }
             __syncwarp();
@@ -297,6 +379,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (p.tma_store && issuer) bulk_wait<0>();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -507,6 +590,11 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     p.relu = a->relu; p.accumulate = a->accumulate;
     p.nf = a->nf; p.den_out = a->den_out;
     p.r1_row = a->r1_row; p.r1_col = a->r1_col;
+    {
+        const int es = a->out_dtype == 1 ? 2 : 4;
+        p.tma_store = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ldo * es) % 16 == 0) ? 1 : 0;
+        if (p.tma_store && (rc = make_tmap_2d(&tm.out, a->out, a->out_dtype, a->rows, a->n_out, a->ldo, nt::BM))) return rc;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {

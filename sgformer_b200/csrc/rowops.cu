@@ -76,6 +76,15 @@ struct Lane {
             }
         }
     }
+    // raw 16-byte loads (kept packed while in flight: software prefetch of the next row costs 4 registers per chunk)
+    __device__ __forceinline__ void load_raw(const T* base, int64_t ld, int64_t r, uint4 (&u)[CPL]) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) u[c] = cval[c] ? ldg_nc_na(base + r * ld + coff[c]) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ __forceinline__ void unpack(const uint4 (&u)[CPL], float (&f)[CPL][Vec16<T>::N]) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) Vec16<T>::unpack(u[c], f[c]);
+    }
     __device__ __forceinline__ void store(T* base, int64_t ld, int64_t r, const float (&f)[CPL][Vec16<T>::N]) const {
 #pragma unroll
         for (int c = 0; c < CPL; ++c)
@@ -85,6 +94,13 @@ struct Lane {
     __device__ __forceinline__ float row_sum(float v) const {
         for (int o = 1; o < lpr; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
+    }
+    // dropout on the lane's chunks of row r (mask = f(seed, row, chunk))
+    __device__ __forceinline__ void dropout(float (&f)[CPL][Vec16<T>::N], uint64_t seed, int64_t r, int chunks, uint32_t thr16,
+                                            float inv_keep) const {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            dropout_chunk<VN>(seed, (uint64_t)r * (uint64_t)chunks + (uint64_t)(coff[c] / VN), thr16, inv_keep, f[c]);
     }
     __device__ __forceinline__ void load_vec(const float* p, float (&f)[CPL][Vec16<T>::N], float fill) const {
 #pragma unroll
@@ -126,7 +142,7 @@ __device__ __forceinline__ void flush_columns(const Lane<T, CPL>& L, float (&acc
 
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kRowBlock) colstats_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int h, int chunks,
+__global__ void __launch_bounds__(kRowBlock, 3) colstats_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int h, int chunks,
                                                               int lpr_log2, const float* __restrict__ w, float* __restrict__ sum,
                                                               float* __restrict__ sumsq) {
     constexpr int VN = Vec16<T>::N;
@@ -134,6 +150,7 @@ __global__ void __launch_bounds__(kRowBlock) colstats_kernel(const T* __restrict
     Lane<T, CPL> L(chunks, lpr_log2);
     float s1[CPL][VN], s2[CPL][VN];
     SGF_ZERO(s1) SGF_ZERO(s2)
+#pragma unroll 1
     for (int64_t r = L.row0; r < rows; r += L.row_step) {
         float f[CPL][VN];
         L.load(x, ldx, r, f);
@@ -146,8 +163,8 @@ __global__ void __launch_bounds__(kRowBlock) colstats_kernel(const T* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm family.  u = a*x + b*r; t = LN?(u); t = relu?(t); y = dropout(t)
-template <typename T, int CPL>
-__global__ void __launch_bounds__(kRowBlock) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ rr, int64_t ld, int64_t rows,
+template <typename T, int CPL, bool DROP>
+__global__ void __launch_bounds__(kRowBlock, 3) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ rr, int64_t ld, int64_t rows,
                                                             int h, int chunks, int lpr_log2, float a, float b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int use_ln,
                                                             int use_relu, float p, uint64_t seed, T* __restrict__ y,
@@ -158,23 +175,38 @@ __global__ void __launch_bounds__(kRowBlock) ln_fwd_kernel(const T* __restrict__
     L.load_vec(use_ln ? gamma : nullptr, g, 1.f);
     L.load_vec(use_ln ? beta : nullptr, be, 0.f);
     const float inv_h = 1.f / (float)h;
-    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    const uint32_t thr16 = dropout_thr16(p);
+    const float inv_keep = dropout_inv_keep(thr16);
     // all lanes of a warp must run the same number of iterations (row_sum shuffles): iterate on the warp's first row
+    uint4 nx[CPL], nr[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; }
+    if (L.row0 < rows) {
+        L.load_raw(x, ld, L.row0, nx);
+        if (rr) L.load_raw(rr, ld, L.row0, nr);
+    }
+#pragma unroll 1
     for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
         const int64_t r = rb + L.grp;
         const bool live = r < rows;
         float u[CPL][VN];
-        if (live) {
-            L.load(x, ld, r, u);
-            if (rr) {
-                float t[CPL][VN];
-                L.load(rr, ld, r, t);
-                SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
-            } else {
-                SGF_FOR_ELEMS u[c][i] = a * u[c][i];
-            }
+        L.unpack(nx, u);
+        if (rr) {
+            float t[CPL][VN];
+            L.unpack(nr, t);
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
         } else {
-            SGF_ZERO(u)
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i];
+        }
+        {
+            const int64_t rn = r + L.row_step;
+            if (rn < rows) {
+                L.load_raw(x, ld, rn, nx);
+                if (rr) L.load_raw(rr, ld, rn, nr);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; }
+            }
         }
         float mean = 0.f, rstd = 1.f;
         if (use_ln) {
@@ -187,7 +219,7 @@ __global__ void __launch_bounds__(kRowBlock) ln_fwd_kernel(const T* __restrict__
             SGF_FOR_ELEMS u[c][i] = (u[c][i] - mean) * rstd * g[c][i] + be[c][i];
         }
         if (use_relu) SGF_FOR_ELEMS u[c][i] = fmaxf(u[c][i], 0.f);
-        if (p > 0.f) SGF_FOR_ELEMS u[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+        if (DROP) L.dropout(u, seed, r, chunks, thr16, inv_keep);
         if (live) {
             L.store(y, ld, r, u);
             if (stats && L.sub == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
@@ -195,8 +227,8 @@ __global__ void __launch_bounds__(kRowBlock) ln_fwd_kernel(const T* __restrict__
     }
 }
 
-template <typename T, int CPL>
-__global__ void __launch_bounds__(kRowBlock) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ rr,
+template <typename T, int CPL, bool DROP>
+__global__ void __launch_bounds__(kRowBlock, 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ rr,
                                                             int64_t ld, int64_t rows, int h, int chunks, int lpr_log2, float a, float b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ stats, int use_ln, int use_relu, float p,
@@ -210,28 +242,48 @@ __global__ void __launch_bounds__(kRowBlock) ln_bwd_kernel(const T* __restrict__
     L.load_vec(use_ln ? beta : nullptr, be, 0.f);
     SGF_ZERO(dg) SGF_ZERO(db)
     const float inv_h = 1.f / (float)h;
-    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    const uint32_t thr16 = dropout_thr16(p);
+    const float inv_keep = dropout_inv_keep(thr16);
+    uint4 nx[CPL], nr[CPL], ng[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; ng[c] = nx[c]; }
+    float nmean = 0.f, nrstd = 1.f;
+    if (L.row0 < rows) {
+        L.load_raw(x, ld, L.row0, nx);
+        if (rr) L.load_raw(rr, ld, L.row0, nr);
+        L.load_raw(dy, ld, L.row0, ng);
+        if (use_ln) { nmean = stats[2 * L.row0]; nrstd = stats[2 * L.row0 + 1]; }
+    }
+#pragma unroll 1
     for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
         const int64_t r = rb + L.grp;
         const bool live = r < rows;
         float u[CPL][VN], gy[CPL][VN];
-        float mean = 0.f, rstd = 1.f;
-        if (live) {
-            L.load(x, ld, r, u);
-            if (rr) {
-                float t[CPL][VN];
-                L.load(rr, ld, r, t);
-                SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
-            } else {
-                SGF_FOR_ELEMS u[c][i] = a * u[c][i];
-            }
-            L.load(dy, ld, r, gy);
-            if (use_ln) { mean = stats[2 * r]; rstd = stats[2 * r + 1]; }
+        const float mean = nmean, rstd = nrstd;
+        L.unpack(nx, u);
+        L.unpack(ng, gy);
+        if (rr) {
+            float t[CPL][VN];
+            L.unpack(nr, t);
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
         } else {
-            SGF_ZERO(u) SGF_ZERO(gy)
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i];
+        }
+        {
+            const int64_t rn = r + L.row_step;
+            if (rn < rows) {
+                L.load_raw(x, ld, rn, nx);
+                if (rr) L.load_raw(rr, ld, rn, nr);
+                L.load_raw(dy, ld, rn, ng);
+                if (use_ln) { nmean = stats[2 * rn]; nrstd = stats[2 * rn + 1]; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; ng[c] = nx[c]; }
+                nmean = 0.f; nrstd = 1.f;
+            }
         }
         SGF_FOR_ELEMS gy[c][i] *= gscale;
-        if (p > 0.f) SGF_FOR_ELEMS gy[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
+        if (DROP) L.dropout(gy, seed, r, chunks, thr16, inv_keep);
         float du[CPL][VN];
         if (use_ln) {
             float s1 = 0.f, s2 = 0.f;
@@ -293,8 +345,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     }
 }
 
-template <typename T, int CPL>
-__global__ void __launch_bounds__(kRowBlock) bn_fwd_kernel(const T* __restrict__ z, const T* __restrict__ res, const T* __restrict__ mix,
+template <typename T, int CPL, bool DROP>
+__global__ void __launch_bounds__(kRowBlock, 3) bn_fwd_kernel(const T* __restrict__ z, const T* __restrict__ res, const T* __restrict__ mix,
                                                             int64_t ld, int64_t rows, int h, int chunks, int lpr_log2,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -314,106 +366,150 @@ __global__ void __launch_bounds__(kRowBlock) bn_fwd_kernel(const T* __restrict__
         L.load_vec(zbias, zb, 0.f);
         SGF_FOR_ELEMS { sc[c][i] = rs[c][i] * g[c][i]; sh[c][i] = be[c][i] + (zb[c][i] - m[c][i]) * sc[c][i]; }
     }
-    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    const uint32_t thr16 = dropout_thr16(p);
+    const float inv_keep = dropout_inv_keep(thr16);
+    uint4 nz[CPL], nr[CPL], nm[CPL];
+    if (L.row0 < rows) {
+        L.load_raw(z, ld, L.row0, nz);
+        if (res) L.load_raw(res, ld, L.row0, nr);
+        if (mix) L.load_raw(mix, ld, L.row0, nm);
+    }
+#pragma unroll 1
     for (int64_t r = L.row0; r < rows; r += L.row_step) {
-        float v[CPL][VN];
-        L.load(z, ld, r, v);
+        float v[CPL][VN], tr[CPL][VN], tm[CPL][VN];
+        L.unpack(nz, v);
+        if (res) L.unpack(nr, tr);
+        if (mix) L.unpack(nm, tm);
+        const int64_t rn = r + L.row_step;
+        if (rn < rows) {
+            L.load_raw(z, ld, rn, nz);
+            if (res) L.load_raw(res, ld, rn, nr);
+            if (mix) L.load_raw(mix, ld, rn, nm);
+        }
         SGF_FOR_ELEMS v[c][i] = v[c][i] * sc[c][i] + sh[c][i];
         if (use_relu) SGF_FOR_ELEMS v[c][i] = fmaxf(v[c][i], 0.f);
-        if (p > 0.f) SGF_FOR_ELEMS v[c][i] *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
-        if (res) {
-            float t[CPL][VN];
-            L.load(res, ld, r, t);
-            SGF_FOR_ELEMS v[c][i] += t[c][i];
-        }
+        if (DROP) L.dropout(v, seed, r, chunks, thr16, inv_keep);
+        if (res) SGF_FOR_ELEMS v[c][i] += tr[c][i];
         if (y_scaled) {
             const float s = row_scale[r];
             float t[CPL][VN];
             SGF_FOR_ELEMS t[c][i] = v[c][i] * s;
             L.store(y_scaled, ld, r, t);
         }
-        if (mix) {
-            float t[CPL][VN];
-            L.load(mix, ld, r, t);
-            SGF_FOR_ELEMS v[c][i] = gw * v[c][i] + (1.f - gw) * t[c][i];
-        }
+        if (mix) SGF_FOR_ELEMS v[c][i] = gw * v[c][i] + (1.f - gw) * tm[c][i];
         if (y) L.store(y, ld, r, v);
     }
 }
 
 // g_raw = gscale * (dy + rs2[r]*dy2);  dres (+)= g_raw;  g = g_raw * dropmask * relumask
 // REDUCE: sums[0:h] += g, sums[h:2h] += g*xhat.   APPLY: dz = BN-backward(g) (* out_scale[r]); dz_colsum += dz (unscaled)
-template <typename T, int CPL, bool APPLY>
-__global__ void __launch_bounds__(kRowBlock) bn_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2,
-                                                            const float* __restrict__ rs2, const T* __restrict__ z, int64_t ld,
-                                                            int64_t rows, int h, int chunks, int lpr_log2, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, const float* __restrict__ zbias, int use_bn,
-                                                            int use_relu, int training, float p, uint64_t seed, float gscale,
-                                                            float* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
-                                                            int dres_acc, float* __restrict__ dz_colsum,
-                                                            const float* __restrict__ out_scale) {
+template <typename T, int CPL, bool APPLY, bool DROP>
+__global__ void __launch_bounds__(kRowBlock, 2) bn_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2,
+                                                               const float* __restrict__ rs2, const T* __restrict__ z, int64_t ld,
+                                                               int64_t rows, int h, int chunks, int lpr_log2, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ zbias, int use_bn,
+                                                               int use_relu, int training, float p, uint64_t seed, float gscale,
+                                                               float* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
+                                                               int dres_acc, float* __restrict__ dz_colsum,
+                                                               const float* __restrict__ out_scale) {
     constexpr int VN = Vec16<T>::N;
     extern __shared__ float sm[];
     Lane<T, CPL> L(chunks, lpr_log2);
-    float m[CPL][VN], rs[CPL][VN], g[CPL][VN], be[CPL][VN];
-    L.load_vec(use_bn ? mean : nullptr, m, 0.f);
-    L.load_vec(use_bn ? rstd : nullptr, rs, 1.f);
-    L.load_vec(use_bn ? gamma : nullptr, g, 1.f);
-    L.load_vec(use_bn ? beta : nullptr, be, 0.f);
+    // per-column constants, folded so that few stay live in the row loop:
+    //   xhat = z*rs + xoff,  pre-activation = z*sc + sh,  dz = sc*g - c0 - c1*z   (sc = gamma*rstd, or 1 without BN)
+    float sc[CPL][VN], sh[CPL][VN], q0[CPL][VN], q1[CPL][VN];   // REDUCE: q0 = rs, q1 = xoff | APPLY: q0 = c0, q1 = c1
     {
-        float zb[CPL][VN];
+        float m[CPL][VN], rs[CPL][VN], g[CPL][VN], be[CPL][VN], zb[CPL][VN];
+        L.load_vec(use_bn ? mean : nullptr, m, 0.f);
+        L.load_vec(use_bn ? rstd : nullptr, rs, 1.f);
+        L.load_vec(use_bn ? gamma : nullptr, g, 1.f);
+        L.load_vec(use_bn ? beta : nullptr, be, 0.f);
         L.load_vec(zbias, zb, 0.f);
-        SGF_FOR_ELEMS m[c][i] -= zb[c][i];  // xhat = (z + zbias - mean) * rstd
+        float m1[CPL][VN], m2[CPL][VN];
+        if (APPLY && use_bn && training) {
+            const float inv_n = 1.f / (float)rows;
+            L.load_vec(sums, m1, 0.f);
+            L.load_vec(sums + h, m2, 0.f);
+            SGF_FOR_ELEMS { m1[c][i] *= inv_n; m2[c][i] *= inv_n; }
+        } else {
+            SGF_ZERO(m1) SGF_ZERO(m2)
+        }
+        SGF_FOR_ELEMS {
+            const float xoff = (zb[c][i] - m[c][i]) * rs[c][i];
+            sc[c][i] = rs[c][i] * g[c][i];
+            sh[c][i] = xoff * g[c][i] + be[c][i];
+            if (APPLY) {
+                q0[c][i] = sc[c][i] * (m1[c][i] + m2[c][i] * xoff);
+                q1[c][i] = sc[c][i] * m2[c][i] * rs[c][i];
+            } else {
+                q0[c][i] = rs[c][i];
+                q1[c][i] = xoff;
+            }
+        }
     }
-    float a1[CPL][VN], a2[CPL][VN];
-    if (APPLY && use_bn && training) {
-        const float inv_n = 1.f / (float)rows;
-        L.load_vec(sums, a1, 0.f);
-        L.load_vec(sums + h, a2, 0.f);
-        SGF_FOR_ELEMS { a1[c][i] *= inv_n; a2[c][i] *= inv_n; }
-    } else {
-        SGF_ZERO(a1) SGF_ZERO(a2)
+    float a1[CPL][VN], a2[CPL][VN];   // REDUCE: sum g, sum g*xhat | APPLY: a1 = column sum of dz
+    SGF_ZERO(a1) SGF_ZERO(a2)
+    const uint32_t thr16 = dropout_thr16(p);
+    const float inv_keep = dropout_inv_keep(thr16);
+    // software pipeline: the next row's 16-byte chunks are in flight (packed) while the current row is processed
+    const bool acc_res = APPLY && dres && dres_acc;
+    uint4 nz[CPL], n1[CPL], n2[CPL], n3[CPL];
+    float ns2 = 1.f;
+    if (L.row0 < rows) {
+        L.load_raw(z, ld, L.row0, nz);
+        if (dy) L.load_raw(dy, ld, L.row0, n1);
+        if (dy2) { L.load_raw(dy2, ld, L.row0, n2); ns2 = rs2 ? rs2[L.row0] : 1.f; }
+        if (acc_res) L.load_raw(dres, ld, L.row0, n3);
     }
-    float cs[CPL][VN];
-    SGF_ZERO(cs)
-    const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+#pragma unroll 1
     for (int64_t r = L.row0; r < rows; r += L.row_step) {
         float gy[CPL][VN], zz[CPL][VN];
-        if (dy) L.load(dy, ld, r, gy);
+        uint4 c3[CPL];
+        const float s2 = ns2;
+        L.unpack(nz, zz);
+        if (dy) L.unpack(n1, gy);
         else SGF_ZERO(gy)
         if (dy2) {
             float t[CPL][VN];
-            L.load(dy2, ld, r, t);
-            const float s2 = rs2 ? rs2[r] : 1.f;
+            L.unpack(n2, t);
             SGF_FOR_ELEMS gy[c][i] += s2 * t[c][i];
+        }
+        if (acc_res) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) c3[c] = n3[c];
+        }
+        const int64_t rn = r + L.row_step;
+        if (rn < rows) {
+            L.load_raw(z, ld, rn, nz);
+            if (dy) L.load_raw(dy, ld, rn, n1);
+            if (dy2) { L.load_raw(dy2, ld, rn, n2); ns2 = rs2 ? rs2[rn] : 1.f; }
+            if (acc_res) L.load_raw(dres, ld, rn, n3);
         }
         SGF_FOR_ELEMS gy[c][i] *= gscale;
         if (APPLY && dres) {
             if (dres_acc) {
                 float t[CPL][VN];
-                L.load(dres, ld, r, t);
+                L.unpack(c3, t);
                 SGF_FOR_ELEMS t[c][i] += gy[c][i];
                 L.store(dres, ld, r, t);
             } else {
                 L.store(dres, ld, r, gy);
             }
         }
-        L.load(z, ld, r, zz);
+        if (DROP) L.dropout(gy, seed, r, chunks, thr16, inv_keep);
         const float os = (APPLY && out_scale) ? out_scale[r] : 1.f;
         SGF_FOR_ELEMS {
-            float xh = (zz[c][i] - m[c][i]) * rs[c][i];
-            float pre = xh * g[c][i] + be[c][i];
+            const float zv = zz[c][i];
             float gg = gy[c][i];
-            if (p > 0.f) gg *= dropout_scale(seed, (uint64_t)r * (uint64_t)h + L.coff[c] + i, p, inv_keep);
-            if (use_relu && pre <= 0.f) gg = 0.f;
+            if (use_relu && zv * sc[c][i] + sh[c][i] <= 0.f) gg = 0.f;
             if (APPLY) {
-                float d = use_bn ? g[c][i] * rs[c][i] * (gg - a1[c][i] - xh * a2[c][i]) : gg;
-                cs[c][i] += L.cval[c] ? d : 0.f;
+                const float d = sc[c][i] * gg - q0[c][i] - q1[c][i] * zv;
+                a1[c][i] += L.cval[c] ? d : 0.f;
                 gy[c][i] = d * os;
             } else {
                 a1[c][i] += gg;
-                a2[c][i] += gg * xh;
+                a2[c][i] += gg * (zv * q0[c][i] + q1[c][i]);
             }
         }
         if (APPLY && dz) L.store(dz, ld, r, gy);
@@ -422,7 +518,7 @@ __global__ void __launch_bounds__(kRowBlock) bn_bwd_kernel(const T* __restrict__
         flush_columns<T, CPL>(L, a1, sm, h, sums);
         flush_columns<T, CPL>(L, a2, sm, h, sums + h);
     } else if (dz_colsum) {
-        flush_columns<T, CPL>(L, cs, sm, h, dz_colsum);
+        flush_columns<T, CPL>(L, a1, sm, h, dz_colsum);
     }
 }
 
@@ -529,6 +625,7 @@ __global__ void __launch_bounds__(kRowBlock) attn_bwd_prep_kernel(const T* __res
                                                                    float* __restrict__ gden) {
     constexpr int VN = Vec16<T>::N;
     Lane<T, CPL> L(chunks, lpr_log2);
+#pragma unroll 1
     for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
         const int64_t r = rb + L.grp;
         const bool live = r < rows;
@@ -666,6 +763,13 @@ using namespace sgf;
         }                                                                                                  \
     } while (0)
 
+// as above plus a compile-time DROP flag (dropout code only in the p > 0 instantiation)
+#define SGF_DISPATCH_T_CPL_DROP(dtype, cpl, drop, KERNEL_CALL)                                             \
+    do {                                                                                                   \
+        if (drop) { constexpr bool DROP = true; SGF_DISPATCH_T_CPL(dtype, cpl, KERNEL_CALL); }             \
+        else { constexpr bool DROP = false; SGF_DISPATCH_T_CPL(dtype, cpl, KERNEL_CALL); }                 \
+    } while (0)
+
 static inline bool geom_for(int dtype, int h, RowGeom& g) {
     if (dtype == 0) return make_geom<float>(h, g);
     if (dtype == 1) return make_geom<__nv_bfloat16>(h, g);
@@ -695,7 +799,7 @@ extern "C" int sgf_ln_fwd(const void* x, const void* r, int64_t ld, int64_t rows
     if (p < 0.f || p >= 1.f) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL(dtype, g.cpl, (ln_fwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, 0, st>>>(
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_fwd_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, 0, st>>>(
                                          (const T*)x, (const T*)r, ld, rows, h, g.chunks, g.lpr_log2, a, b, gamma, beta, use_ln,
                                          use_relu, p, seed, (T*)y, stats)));
     SGF_LAUNCH_CHECK(); count_launch();
@@ -712,7 +816,7 @@ extern "C" int sgf_ln_bwd(const void* dy, const void* x, const void* r, int64_t 
     if (use_ln && (!gamma || !beta || !stats)) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL(dtype, g.cpl, (ln_bwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)x, (const T*)r, ld, rows, h, g.chunks, g.lpr_log2, a, b, gamma, beta,
                                          stats, use_ln, use_relu, p, seed, gscale, (T*)dx, (T*)dr, dgamma, dbeta)));
     SGF_LAUNCH_CHECK(); count_launch();
@@ -743,7 +847,7 @@ extern "C" int sgf_bn_fwd(const void* z, const void* res, const void* mix, int64
     if (p < 0.f || p >= 1.f) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_fwd_kernel<T, CPL><<<row_grid(rows, g), kRowBlock, 0, st>>>(
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (bn_fwd_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, 0, st>>>(
                                          (const T*)z, (const T*)res, (const T*)mix, ld, rows, h, g.chunks, g.lpr_log2, mean, rstd,
                                          gamma, beta, zbias, use_bn, use_relu, p, seed, gw, row_scale, (T*)y, (T*)y_scaled)));
     SGF_LAUNCH_CHECK(); count_launch();
@@ -761,7 +865,7 @@ extern "C" int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* r
     if (use_bn && (!mean || !rstd || !gamma || !beta)) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_bwd_kernel<T, CPL, false><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (bn_bwd_kernel<T, CPL, false, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
                                          rstd, gamma, beta, zbias, use_bn, use_relu, 1, p, seed, gscale, sums, (T*)nullptr,
                                          (T*)nullptr, 0, (float*)nullptr, (const float*)nullptr)));
@@ -782,7 +886,7 @@ extern "C" int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* ro
     if (use_bn && training && !sums) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL(dtype, g.cpl, (bn_bwd_kernel<T, CPL, true><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (bn_bwd_kernel<T, CPL, true, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
                                          rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale,
                                          const_cast<float*>(sums), (T*)dz, (T*)dres, dres_accumulate, dz_colsum, out_row_scale)));

@@ -321,8 +321,12 @@ def colstats(x: Tensor, w: Optional[Tensor] = None, want_sum: bool = True, want_
     rows, h, ld = _mat(x, "x")
     s = torch.zeros(h, dtype=torch.float32, device=x.device) if want_sum else None
     q = torch.zeros(h, dtype=torch.float32, device=x.device) if want_sumsq else None
-    check(lib().sgf_colstats(_p(x), ld, rows, h, dcode(x), _p(_f32vec(w, rows, "w")), _p(s), _p(q), _stream()),
-          "sgf_colstats")
+    wv = _f32vec(w, rows, "w")
+    blk = 2048 // x.element_size()      # the row kernels cover at most 2 KB of a row per launch
+    for c0 in range(0, h, blk):
+        c1 = min(h, c0 + blk)
+        check(lib().sgf_colstats(_p(x[:, c0:c1]), ld, rows, c1 - c0, dcode(x), _p(wv), _p(s[c0:c1] if s is not None else None),
+                                 _p(q[c0:c1] if q is not None else None), _stream()), "sgf_colstats")
     return s, q
 
 
