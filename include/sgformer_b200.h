@@ -57,6 +57,12 @@ int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes /* host out */)
 int sgf_csr_build(const int64_t* edge_index /* [2,nnz] */, int64_t nnz, int64_t n, int by_source,
                   int self_loop_mode, int64_t* rowptr /* [n+1] */, int32_t* col, float* dinv /* [n] or NULL */,
                   void* ws, size_t ws_bytes, void* stream);
+/* Row shard of the same CSR: only rows [row_begin, row_end) of the n_cols x n_cols pattern are built (local row =
+ * global row - row_begin), column ids stay global.  Used when the nodes are row-sharded across GPUs:
+ * every rank builds its own rows from the full edge list.  ws sized by sgf_csr_build_ws_bytes(nnz, row_end-row_begin). */
+int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
+                       int by_source, int self_loop_mode, int64_t* rowptr, int32_t* col, float* dinv, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* K9 — induced subgraph with relabelling (replaces PyG subgraph(idx, edge_index, num_nodes=n,
  * relabel_nodes=True) at large/main-batch.py:139 / large/eval.py:89): keeps edges whose endpoints are
@@ -180,8 +186,9 @@ int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* row_scale2, 
 int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld,
                      int64_t rows, int h, int dtype, const float* mean, const float* rstd, const float* gamma,
                      const float* beta, const float* zbias, int use_bn, int use_relu, int training, float p,
-                     uint64_t seed, float gscale, const float* sums, void* dz, void* dres, int dres_accumulate,
-                     float* dz_colsum, const float* out_row_scale, void* stream);
+                     uint64_t seed, float gscale, int64_t stat_rows /* rows the batch statistics span; 0 = rows (the
+                     global node count when row-sharded and `sums` was all-reduced) */, const float* sums, void* dz,
+                     void* dres, int dres_accumulate, float* dz_colsum, const float* out_row_scale, void* stream);
 
 /* out = (a*x + b*y) * row_scale[r]  (y, row_scale nullable; y has x's dtype); in/out dtypes may differ (casts). */
 int sgf_axpby(const void* x, int64_t ldx, int x_dtype, const void* y, int64_t ldy, int y_dtype, float a, float b,

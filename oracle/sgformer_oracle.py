@@ -194,11 +194,11 @@ def gcn_degree_inv_sqrt(edge_index: Tensor, n: int) -> Tensor:
     return torch.where(d > 0, dinv, torch.zeros_like(dinv))
 
 
-def normalized_adjacency(edge_index: Tensor, n: int) -> Tensor:
+def normalized_adjacency(edge_index: Tensor, n: int, dtype=torch.float32) -> Tensor:
     """Â as a torch CSR tensor: Â[c, r] += w_e for each edge e=(r -> c), w_e = d[c]^-1/2 d[r]^-1/2
     (large/ours.py:29-33: SparseTensor(row=col, col=row, value=w)); duplicates accumulate."""
     row, col = edge_index[0], edge_index[1]
-    d = torch.bincount(col, minlength=n).to(torch.float32)
+    d = torch.bincount(col, minlength=n).to(dtype)     # the reference uses fp32; fp64 only for accuracy studies in tests
     w = (1.0 / d[col]).sqrt() * (1.0 / d[row]).sqrt()
     w = torch.nan_to_num(w, nan=0.0, posinf=0.0, neginf=0.0)
     a = torch.sparse_coo_tensor(torch.stack([col, row]), w, (n, n)).coalesce()
@@ -239,7 +239,7 @@ def graph_conv(x: Tensor, edge_index: Tensor, sd: Dict[str, Tensor], cfg: dict, 
     always adds the input-MLP output x0 (:83, :92-93)."""
     n = x.shape[0]
     p = cfg["gnn_dropout"]
-    adj = normalized_adjacency(edge_index, n)
+    adj = normalized_adjacency(edge_index, n, x.dtype)
     x = F.linear(x, sd[pfx + "fcs.0.weight"], sd[pfx + "fcs.0.bias"])
     if cfg["gnn_use_bn"]:
         x = _batch_norm(x, sd, pfx + "bns.0.", training, stats_out)

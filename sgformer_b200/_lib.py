@@ -53,6 +53,7 @@ _SIGS = {
     "sgf_set_device": (C.c_int, [C.c_int]),
     "sgf_csr_build_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "sgf_csr_build": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sgf_csr_build_rect": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_subgraph_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "sgf_subgraph": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_spmm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp]),
@@ -70,7 +71,7 @@ _SIGS = {
     "sgf_bn_bwd_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
                                     C.c_int, _f32, _u64, _f32, _vp, _vp]),
     "sgf_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int,
-                                   C.c_int, C.c_int, _f32, _u64, _f32, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+                                   C.c_int, C.c_int, _f32, _u64, _f32, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "sgf_axpby": (C.c_int, [_vp, _i64, C.c_int, _vp, _i64, C.c_int, _f32, _f32, _vp, _vp, _i64, C.c_int, _i64, C.c_int,
                             _vp]),
     "sgf_pack_operand": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, _vp, _i64, C.c_int, _i64, _vp, _vp]),

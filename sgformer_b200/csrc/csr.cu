@@ -21,14 +21,17 @@ namespace sgf {
 constexpr int kScanBlock = 1024;
 constexpr int kScanItems = 4;  // per thread -> 4096 per block
 
+// rows [row_begin, row_end) of a matrix with n_cols columns are built; edges whose key falls outside are skipped
 __global__ void csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                 int64_t n, int drop_self_loops, int* __restrict__ counts, int* __restrict__ err) {
+                                 int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
+                                 int* __restrict__ counts, int* __restrict__ err) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
         int64_t k = key[e], v = val[e];
-        if (k < 0 || k >= n || v < 0 || v >= n) { atomicExch(err, 1); continue; }
+        if (k < 0 || k >= n_cols || v < 0 || v >= n_cols) { atomicExch(err, 1); continue; }
+        if (k < row_begin || k >= row_end) continue;
         if (drop_self_loops && k == v) continue;
-        atomicAdd(&counts[k], 1);
+        atomicAdd(&counts[k - row_begin], 1);
     }
 }
 
@@ -123,25 +126,26 @@ __global__ void scan_add_kernel(int64_t* __restrict__ rowptr, int64_t n, const i
     }
 }
 
-__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz, int64_t n,
-                                int drop_self_loops, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
-                                int32_t* __restrict__ col) {
+__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+                                int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
+                                const int64_t* __restrict__ rowptr, int* __restrict__ cursor, int32_t* __restrict__ col) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
         int64_t k = key[e], v = val[e];
-        if (k < 0 || k >= n || v < 0 || v >= n) continue;
+        if (k < row_begin || k >= row_end || v < 0 || v >= n_cols) continue;
         if (drop_self_loops && k == v) continue;
+        k -= row_begin;
         int pos = atomicAdd(&cursor[k], 1);
         col[rowptr[k] + pos] = (int32_t)v;
     }
 }
 
-__global__ void csr_add_loops_kernel(int64_t n, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
+__global__ void csr_add_loops_kernel(int64_t n, int64_t row_begin, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
                                      int32_t* __restrict__ col) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int pos = atomicAdd(&cursor[i], 1);
-        col[rowptr[i] + pos] = (int32_t)i;
+        col[rowptr[i] + pos] = (int32_t)(row_begin + i);
     }
 }
 
@@ -389,9 +393,13 @@ extern "C" int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
     return SGF_OK;
 }
 
-extern "C" int sgf_csr_build(const int64_t* edge_index, int64_t nnz, int64_t n, int by_source, int self_loop_mode,
-                             int64_t* rowptr, int32_t* col, float* dinv, void* ws, size_t ws_bytes, void* stream) {
-    if (nnz < 0 || n < 0 || n >= (int64_t)INT32_MAX || !rowptr || (!col && nnz + n > 0) || !ws) return SGF_ERR_ARG;
+extern "C" int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
+                                  int by_source, int self_loop_mode, int64_t* rowptr, int32_t* col, float* dinv, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    const int64_t n = row_end - row_begin;
+    if (nnz < 0 || n < 0 || row_begin < 0 || row_end > n_cols || n_cols >= (int64_t)INT32_MAX || !rowptr ||
+        (!col && nnz + n > 0) || !ws)
+        return SGF_ERR_ARG;
     if (nnz > 0 && !edge_index) return SGF_ERR_ARG;
     if (self_loop_mode != 0 && self_loop_mode != 1) return SGF_ERR_ARG;
     CsrWs w = carve_ws(ws, nnz, n);
@@ -402,17 +410,17 @@ extern "C" int sgf_csr_build(const int64_t* edge_index, int64_t nnz, int64_t n, 
     SGF_CUDA_TRY(cudaMemsetAsync(w.counts, 0, (size_t)(n + 1) * 4, st));
     SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
     if (nnz > 0) {
-        csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, n, self_loop_mode, w.counts, w.err);
+        csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, w.counts, w.err);
         SGF_LAUNCH_CHECK(); count_launch();
     }
     int rc = launch_scan(w.counts, n, self_loop_mode, rowptr, w.block_sums, w.total, w.cursor, st);
     if (rc) return rc;
     if (nnz > 0) {
-        csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, n, self_loop_mode, rowptr, w.cursor, col);
+        csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, rowptr, w.cursor, col);
         SGF_LAUNCH_CHECK(); count_launch();
     }
     if (self_loop_mode == 1 && n > 0) {
-        csr_add_loops_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, rowptr, w.cursor, col);
+        csr_add_loops_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, row_begin, rowptr, w.cursor, col);
         SGF_LAUNCH_CHECK(); count_launch();
     }
     if (n > 0) {
@@ -435,6 +443,11 @@ extern "C" int sgf_csr_build(const int64_t* edge_index, int64_t nnz, int64_t n, 
         SGF_CUDA_TRY(cudaMemsetAsync(rowptr, 0, 8, st));
     }
     return SGF_OK;
+}
+
+extern "C" int sgf_csr_build(const int64_t* edge_index, int64_t nnz, int64_t n, int by_source, int self_loop_mode,
+                             int64_t* rowptr, int32_t* col, float* dinv, void* ws, size_t ws_bytes, void* stream) {
+    return sgf_csr_build_rect(edge_index, nnz, 0, n, n, by_source, self_loop_mode, rowptr, col, dinv, ws, ws_bytes, stream);
 }
 
 // workspace: flags int32[nnz] | pos int64[nnz+1] | block_sums | total

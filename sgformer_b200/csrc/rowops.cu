@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(kRowBlock, 2) bn_bwd_kernel(const T* __restric
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, const float* __restrict__ zbias, int use_bn,
                                                                int use_relu, int training, float p, uint64_t seed, float gscale,
-                                                               float* __restrict__ sums, T* __restrict__ dz, T* __restrict__ dres,
+                                                               int64_t stat_rows, float* __restrict__ sums, T* __restrict__ dz,
+                                                               T* __restrict__ dres,
                                                                int dres_acc, float* __restrict__ dz_colsum,
                                                                const float* __restrict__ out_scale) {
     constexpr int VN = Vec16<T>::N;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kRowBlock, 2) bn_bwd_kernel(const T* __restric
         L.load_vec(zbias, zb, 0.f);
         float m1[CPL][VN], m2[CPL][VN];
         if (APPLY && use_bn && training) {
-            const float inv_n = 1.f / (float)rows;
+            const float inv_n = 1.f / (float)(stat_rows > 0 ? stat_rows : rows);
             L.load_vec(sums, m1, 0.f);
             L.load_vec(sums + h, m2, 0.f);
             SGF_FOR_ELEMS { m1[c][i] *= inv_n; m2[c][i] *= inv_n; }
@@ -867,8 +868,8 @@ extern "C" int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* r
     cudaStream_t st = (cudaStream_t)stream;
     SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (bn_bwd_kernel<T, CPL, false, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
-                                         rstd, gamma, beta, zbias, use_bn, use_relu, 1, p, seed, gscale, sums, (T*)nullptr,
-                                         (T*)nullptr, 0, (float*)nullptr, (const float*)nullptr)));
+                                         rstd, gamma, beta, zbias, use_bn, use_relu, 1, p, seed, gscale, (int64_t)0, sums,
+                                         (T*)nullptr, (T*)nullptr, 0, (float*)nullptr, (const float*)nullptr)));
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }
@@ -876,8 +877,8 @@ extern "C" int sgf_bn_bwd_reduce(const void* dy, const void* dy2, const float* r
 extern "C" int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* row_scale2, const void* z, int64_t ld, int64_t rows,
                                 int h, int dtype, const float* mean, const float* rstd, const float* gamma, const float* beta,
                                 const float* zbias, int use_bn, int use_relu, int training, float p, uint64_t seed, float gscale,
-                                const float* sums, void* dz, void* dres, int dres_accumulate, float* dz_colsum,
-                                const float* out_row_scale, void* stream) {
+                                int64_t stat_rows, const float* sums, void* dz, void* dres, int dres_accumulate,
+                                float* dz_colsum, const float* out_row_scale, void* stream) {
     RowGeom g;
     if (!geom_for(dtype, h, g) || !aligned16(dy) || !aligned16(dy2) || !aligned16(z) || !aligned16(dz) || !aligned16(dres) ||
         !ld_ok(dtype, ld) || rows < 0 || (!dy && !dy2))
@@ -888,7 +889,7 @@ extern "C" int sgf_bn_bwd_apply(const void* dy, const void* dy2, const float* ro
     cudaStream_t st = (cudaStream_t)stream;
     SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (bn_bwd_kernel<T, CPL, true, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)dy2, row_scale2, (const T*)z, ld, rows, h, g.chunks, g.lpr_log2, mean,
-                                         rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale,
+                                         rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale, stat_rows,
                                          const_cast<float*>(sums), (T*)dz, (T*)dres, dres_accumulate, dz_colsum, out_row_scale)));
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;

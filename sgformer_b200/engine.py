@@ -20,6 +20,7 @@ import torch
 
 from . import kernels as K
 from ._lib import EPI_ATTN_APPLY
+from .dist import SINGLE, Comm
 from .graph import Graph
 
 Tensor = torch.Tensor
@@ -81,41 +82,47 @@ def input_operand(x: Tensor, prec: Precision) -> K.Operand:
 # =================================================================================================
 # linear attention core (full_attention_conv)
 # =================================================================================================
-def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precision, tape: Optional[Tape]) -> Tensor:
+def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precision, tape: Optional[Tape],
+                      comm: Comm = SINGLE) -> Tensor:
     """q,k: [N, H*M], v: [N, H*D] activations (views allowed) -> o [N, H*D].  medium/ours.py:14-34.
-    One Frobenius norm over all heads (medium/ours.py:16-17); N is the query count."""
-    n = q.shape[0]
+    One Frobenius norm over all heads (medium/ours.py:16-17); N is the query count (the GLOBAL node count when the rows
+    are sharded: the un-normalised partials {S', z', ||q||^2, ||k||^2} are all-reduced once, C1)."""
+    n_loc = q.shape[0]
+    n = comm.n_global if comm.active else n_loc
     m = q.shape[1] // heads
     d = v.shape[1] // heads
     dev = q.device
     _, sq_q = K.colstats(q, want_sum=False)
     z_raw, sq_k = K.colstats(k)
-    o = K.alloc_act(n, heads * d, q.dtype, dev)
-    den = torch.empty((heads, n), dtype=torch.float32, device=dev)
-    s_list, scal = [], None
+    s_list = []
     for hd in range(heads):
-        qh, kh, vh = q[:, hd * m:(hd + 1) * m], k[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
+        kh, vh = k[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
         s_raw = torch.empty((m, d), dtype=torch.float32, device=dev)
         K.gemm_tn(K.as_operand(kh, prec.planes), K.as_operand(vh, prec.planes), s_raw)
-        bmat, btail, scal = K.attn_prepare_fwd(s_raw, z_raw[hd * m:(hd + 1) * m], sq_q, sq_k, prec.planes)
+        s_list.append(s_raw)
+    comm.allreduce_(sq_q, z_raw, sq_k, *s_list)
+    o = K.alloc_act(n_loc, heads * d, q.dtype, dev)
+    den = torch.empty((heads, n_loc), dtype=torch.float32, device=dev)
+    scal = None
+    for hd in range(heads):
+        qh, vh = q[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
+        bmat, btail, scal = K.attn_prepare_fwd(s_list[hd], z_raw[hd * m:(hd + 1) * m], sq_q, sq_k, prec.planes)
         K.gemm_nt([K.as_operand(qh, prec.planes)], [bmat], [(0, 0, 0, 0, m)], d, o[:, hd * d:(hd + 1) * d],
                   epi=EPI_ATTN_APPLY, aux=vh, tail=btail, nf=float(n), den_out=den[hd])
-        s_list.append(s_raw)
     if tape is not None:
-        tape.update(q=q, k=k, v=v, o=o, den=den, s=s_list, z=z_raw, scal=scal, heads=heads, m=m, d=d)
+        tape.update(q=q, k=k, v=v, o=o, den=den, s=s_list, z=z_raw, scal=scal, heads=heads, m=m, d=d, n=n)
     return o
 
 
 def attention_backward(tape: Tape, g: Tensor, gscale: float, prec: Precision, dq: Tensor, dk: Tensor,
-                       dv: Optional[Tensor], dv_accumulate: bool = False):
+                       dv: Optional[Tensor], dv_accumulate: bool = False, comm: Comm = SINGLE):
     """g = dL/do [N, H*D] (times gscale).  Writes dq, dk [N, H*M] and dv [N, H*D] (+= if dv_accumulate).
-    SURVEY.md Appendix A.1 in the raw-q/k form documented at sgf_attn_prepare_bwd."""
+    SURVEY.md Appendix A.1 in the raw-q/k form documented at sgf_attn_prepare_bwd; row-sharded: {dS', dz'} all-reduced (C2)."""
     q, k, v, o, den = tape["q"], tape["k"], tape["v"], tape["o"], tape["den"]
-    heads, m, d = tape["heads"], tape["m"], tape["d"]
-    n = q.shape[0]
+    heads, m, d, n = tape["heads"], tape["m"], tape["d"], tape["n"]
     dev = q.device
     scal_bwd = torch.zeros((heads, 8), dtype=torch.float32, device=dev)
-    per_head = []
+    part = []
     for hd in range(heads):
         qh = q[:, hd * m:(hd + 1) * m]
         gnum, gden = K.attn_bwd_prep(g[:, hd * d:(hd + 1) * d], o[:, hd * d:(hd + 1) * d], den[hd], gscale)
@@ -123,6 +130,11 @@ def attention_backward(tape: Tape, g: Tensor, gscale: float, prec: Precision, dq
         ds_raw = torch.empty((m, d), dtype=torch.float32, device=dev)
         K.gemm_tn(K.as_operand(qh, prec.planes), gnum_op, ds_raw)
         dz_raw, _ = K.colstats(qh, w=gden, want_sumsq=False)
+        part.append((gnum, gden, gnum_op, ds_raw, dz_raw))
+    comm.allreduce_(*[t for p_ in part for t in (p_[3], p_[4])])
+    per_head = []
+    for hd in range(heads):
+        gnum, gden, gnum_op, ds_raw, dz_raw = part[hd]
         ops = K.attn_prepare_bwd(tape["s"][hd], tape["z"][hd * m:(hd + 1) * m], ds_raw, dz_raw, tape["scal"], prec.planes,
                                  scal_bwd[hd])
         per_head.append((gnum, gden, gnum_op, ops))
@@ -160,7 +172,7 @@ def _qkv_weight(P, pfx: str, use_weight: bool) -> (Tensor, Tensor):
 
 
 def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precision, training: bool, seed: int,
-                  tape: Optional[Tape], pfx: str = "trans_conv.") -> Tensor:
+                  tape: Optional[Tape], pfx: str = "trans_conv.", comm: Comm = SINGLE) -> Tensor:
     h, H, d_in = cfg["hidden"], cfg["num_heads"], cfg["in_channels"]
     n = xin.rows
     dev = xin.data.device
@@ -186,7 +198,7 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
         q, k = qkv[:, :H * h], qkv[:, H * h:2 * H * h]
         v = qkv[:, 2 * H * h:] if use_weight else x
         at = Tape() if tape is not None else None
-        o = attention_forward(q, k, v, H, prec, at)
+        o = attention_forward(q, k, v, H, prec, at, comm)
         a = K.head_mean(o, H, h) if H > 1 else o
         y, st = K.ln_fwd(a, x if use_res else None, ca, cb, P.get(f"{pfx}bns.{i + 1}.weight"), P.get(f"{pfx}bns.{i + 1}.bias"),
                          use_ln, bool(cfg["trans_use_act"]), p, seed + 211 + i, tape is not None)
@@ -197,7 +209,7 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
 
 
 def trans_backward(P, cfg: dict, tape: Tape, dout: Tensor, gscale: float, prec: Precision, grads: Dict[str, Tensor],
-                   pfx: str = "trans_conv.", want_dx: bool = False) -> Optional[Tensor]:
+                   pfx: str = "trans_conv.", want_dx: bool = False, comm: Comm = SINGLE) -> Optional[Tensor]:
     h, H, d_in = cfg["hidden"], cfg["num_heads"], cfg["in_channels"]
     n, p, seed = tape["n"], tape["p"], tape["seed"]
     dev = dout.device
@@ -229,11 +241,12 @@ def trans_backward(P, cfg: dict, tape: Tape, dout: Tensor, gscale: float, prec: 
             first_write = False
         g_all = da if H == 1 else _tile_heads(da, H)
         if use_weight:
-            attention_backward(at, g_all, 1.0 / H, prec, dqkv[:, :H * h], dqkv[:, H * h:2 * H * h], dqkv[:, 2 * H * h:])
+            attention_backward(at, g_all, 1.0 / H, prec, dqkv[:, :H * h], dqkv[:, H * h:2 * H * h], dqkv[:, 2 * H * h:],
+                               comm=comm)
         else:
             # V is the layer input itself: its gradient goes straight into dprev
             attention_backward(at, g_all, 1.0 / H, prec, dqkv[:, :H * h], dqkv[:, H * h:2 * H * h], dprev,
-                               dv_accumulate=not first_write)
+                               dv_accumulate=not first_write, comm=comm)
             first_write = False
         wcat, _ = _qkv_weight(P, lp, use_weight)
         dqkv_op = K.as_operand(dqkv, prec.planes)
@@ -276,13 +289,15 @@ def _tile_heads(da: Tensor, heads: int) -> Tensor:
 # =================================================================================================
 # GraphConv branch (large / 100M)
 # =================================================================================================
-def _bn_stats(z: Tensor, P, name: str, use_bn: bool, training: bool, zbias: Optional[Tensor] = None):
+def _bn_stats(z: Tensor, P, name: str, use_bn: bool, training: bool, zbias: Optional[Tensor] = None, comm: Comm = SINGLE):
     if not use_bn:
         return None, None
     h = z.shape[1]
     if training:
         s, q = K.colstats(z)
-        mean, rstd = K.bn_finalize(s, q, z.shape[0], h, zbias, P.get(name + "running_mean"), P.get(name + "running_var"),
+        comm.allreduce_(s, q)                                              # C3: batch statistics span all shards
+        rows = comm.n_global if comm.active else z.shape[0]
+        mean, rstd = K.bn_finalize(s, q, rows, h, zbias, P.get(name + "running_mean"), P.get(name + "running_var"),
                                    z.device)
         nbt = P.get(name + "num_batches_tracked")
         if nbt is not None:
@@ -294,7 +309,8 @@ def _bn_stats(z: Tensor, P, name: str, use_bn: bool, training: bool, zbias: Opti
 
 
 def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, training: bool, seed: int,
-                  tape: Optional[Tape], mix: Optional[Tensor] = None, gw: float = 1.0, pfx: str = "graph_conv.") -> Tensor:
+                  tape: Optional[Tape], mix: Optional[Tensor] = None, gw: float = 1.0, pfx: str = "graph_conv.",
+                  comm: Comm = SINGLE) -> Tensor:
     """Returns GraphConv(x) — or, when `mix` is given, gw*GraphConv(x) + (1-gw)*mix (the SGFormer branch sum fused
     into the last layer's epilogue pass)."""
     h, d_in, nl = cfg["hidden"], cfg["in_channels"], cfg["gnn_num_layers"]
@@ -306,7 +322,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     dinv = graph.dinv
     z0 = K.gemm_nt([xin], [_w(P, pfx + "fcs.0.weight", prec)], [(0, 0, 0, 0, d_in)], h,
                    K.alloc_act(n, h, prec.act_dtype, dev), bias=P[pfx + "fcs.0.bias"])
-    mean0, rstd0 = _bn_stats(z0, P, pfx + "bns.0.", use_bn, training)
+    mean0, rstd0 = _bn_stats(z0, P, pfx + "bns.0.", use_bn, training, comm=comm)
     last_is_input = nl == 0
     x0, cur_s = K.bn_fwd(z0, None, mix if last_is_input else None, mean0, rstd0, P.get(pfx + "bns.0.weight"),
                          P.get(pfx + "bns.0.bias"), None, use_bn, True, p, seed + 307, gw, dinv, True, not last_is_input)
@@ -316,7 +332,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     out = x0
     for i in range(nl):
         last = i == nl - 1
-        y = K.spmm(graph.rowptr, graph.col, dinv, cur_s)
+        y = K.spmm(graph.rowptr, graph.col, dinv, comm.allgather_rows(cur_s))    # C4: operand rows of every shard
         if use_init:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
             z = K.gemm_nt([K.as_operand(y, prec.planes), K.as_operand(x0, prec.planes)], [w],
@@ -328,7 +344,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
         else:
             z = y
         name = f"{pfx}bns.{i + 1}."
-        mean, rstd = _bn_stats(z, P, name, use_bn, training)
+        mean, rstd = _bn_stats(z, P, name, use_bn, training, comm=comm)
         yo, ys = K.bn_fwd(z, x0 if use_res else None, mix if last else None, mean, rstd, P.get(name + "weight"),
                           P.get(name + "bias"), None, use_bn, use_act, p, seed + 401 + i, gw, dinv, last, not last)
         if tape is not None:
@@ -341,7 +357,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
 
 
 def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: Precision, grads: Dict[str, Tensor],
-                   pfx: str = "graph_conv.", want_dx: bool = False) -> Optional[Tensor]:
+                   pfx: str = "graph_conv.", want_dx: bool = False, comm: Comm = SINGLE) -> Optional[Tensor]:
     """dout = gradient w.r.t. the tensor gconv_forward returned (the mixed tensor when `mix` was given: the factor gw
     is applied here; the caller routes (1-gw)*dout to the other branch)."""
     h, d_in, nl = cfg["hidden"], cfg["in_channels"], cfg["gnn_num_layers"]
@@ -352,6 +368,8 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
     dinv = graph.dinv
     rowptr_t, col_t = graph.transpose()
     x0 = tape["x0"]
+    red = comm.allreduce_ if comm.active else None
+    nstat = comm.n_global if comm.active else 0
     gs = tape["gw"] if tape["mixed"] else 1.0
     dx0 = None            # accumulated gradient of x0 (act dtype)
     dy_plain, dy_scaled = dout, None   # gradient entering the current layer's epilogue: plain, or pre-SpMM (needs *dinv)
@@ -366,10 +384,11 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
         dz, sums, colsum = K.bn_bwd(dy_plain, dy_scaled, dinv if dy_scaled is not None else None, L["z"], L["mean"],
                                     L["rstd"], P.get(name + "weight"), P.get(name + "bias"), None, use_bn, use_act, training,
                                     p, seed + 401 + i, gs, dres=dx0 if use_res else None, dres_accumulate=res_acc,
-                                    want_dz_colsum=use_init or use_weight)
+                                    want_dz_colsum=use_init or use_weight, reduce_fn=red, stat_rows=nstat)
         gs = 1.0
         if use_bn and training:
             grads[name + "bias"], grads[name + "weight"] = sums[:h], sums[h:]
+            _mark_global(grads, comm, name + "bias", name + "weight")     # the BN sums were all-reduced between the phases
         elif use_bn:
             grads[name + "bias"], grads[name + "weight"] = _eval_bn_param_grads(dy_plain, dy_scaled, dinv, L, P, name, use_act)
         if use_init or use_weight:
@@ -393,7 +412,8 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
                     K.gemm_nt([dz_op], [_slice_rows(wt, h, 2 * h)], [(0, 0, 0, 0, h)], h, dx0, accumulate=True)
         else:
             dys = K.axpby(dz, None, 1.0, 0.0, row_scale=dinv)
-        dy_scaled = K.spmm(rowptr_t, col_t, None, dys)   # = A^T (dinv . dy): gradient w.r.t. the pre-scaled SpMM input
+        # = A^T (dinv . dy): gradient w.r.t. the pre-scaled SpMM input (C4: gradient rows of every shard)
+        dy_scaled = K.spmm(rowptr_t, col_t, None, comm.allgather_rows(dys))
         dy_plain = None
     # input layer epilogue: gradient of x0 = accumulated dx0 (+ dinv * dy_scaled from layer 0's SpMM)
     if nl == 0:
@@ -402,9 +422,10 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
         g_plain, g_scaled = dx0, dy_scaled
     dz0, sums, colsum = K.bn_bwd(g_plain, g_scaled, dinv if g_scaled is not None else None, tape["z0"], tape["mean0"],
                                  tape["rstd0"], P.get(pfx + "bns.0.weight"), P.get(pfx + "bns.0.bias"), None, use_bn, True,
-                                 training, p, seed + 307, gs, want_dz_colsum=True)
+                                 training, p, seed + 307, gs, want_dz_colsum=True, reduce_fn=red, stat_rows=nstat)
     if use_bn and training:
         grads[pfx + "bns.0.bias"], grads[pfx + "bns.0.weight"] = sums[:h], sums[h:]
+        _mark_global(grads, comm, pfx + "bns.0.bias", pfx + "bns.0.weight")
     elif use_bn:
         grads[pfx + "bns.0.bias"], grads[pfx + "bns.0.weight"] = _eval_bn_param_grads(
             g_plain, g_scaled, dinv, dict(z=tape["z0"], mean=tape["mean0"], rstd=tape["rstd0"]), P, pfx + "bns.0.", True)
@@ -418,6 +439,12 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
         K.gemm_nt([dz0_op], [_w(P, pfx + "fcs.0.weight", prec, transpose=True)], [(0, 0, 0, 0, h)], d_in, dx)
         return dx
     return None
+
+
+def _mark_global(grads: dict, comm: Comm, *names: str):
+    """Gradients that are already sums over all shards (excluded from the C5 all-reduce)."""
+    if comm.active:
+        grads.setdefault("__global__", set()).update(names)
 
 
 def _eval_bn_param_grads(dy, dy2, dinv, L, P, name, use_relu):
@@ -436,7 +463,8 @@ def _slice_rows(op: K.Operand, r0: int, r1: int) -> K.Operand:
 # GCN backbone (medium): PyG GCNConv stack
 # =================================================================================================
 def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, training: bool, seed: int,
-                tape: Optional[Tape], mix: Optional[Tensor] = None, gw: float = 1.0, pfx: str = "gnn.") -> Tensor:
+                tape: Optional[Tape], mix: Optional[Tensor] = None, gw: float = 1.0, pfx: str = "gnn.",
+                comm: Comm = SINGLE) -> Tensor:
     """models.GCN.forward (medium/models.py:49-63).  `graph` is built with PyG self-loop semantics (gcn_norm)."""
     nl = cfg["gcn_num_layers"]
     n = xin.rows
@@ -453,14 +481,14 @@ def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, tra
         hout = P[wname].shape[0]
         t = K.gemm_nt([cur_op], [_w(P, wname, prec)], [(0, 0, 0, 0, cur_k)], hout, K.alloc_act(n, hout, prec.act_dtype, dev),
                       row_scale=dinv)
-        s = K.spmm(graph.rowptr, graph.col, dinv, t)
+        s = K.spmm(graph.rowptr, graph.col, dinv, comm.allgather_rows(t))
         zb = P.get(f"{pfx}convs.{i}.bias")
         if last:
             out, _ = K.bn_fwd(s, None, mix, None, None, None, None, zb, False, False, 0.0, 0, gw, None, True, False)
             layers.append(dict(s=s, cur_op=cur_op, cur_k=cur_k, hout=hout))
         else:
             name = f"{pfx}bns.{i}."
-            mean, rstd = _bn_stats(s, P, name, use_bn, training, zbias=zb) if use_bn else (None, None)
+            mean, rstd = _bn_stats(s, P, name, use_bn, training, zbias=zb, comm=comm) if use_bn else (None, None)
             y, _ = K.bn_fwd(s, None, None, mean, rstd, P.get(name + "weight"), P.get(name + "bias"), zb, use_bn, True, p,
                             seed + 503 + i, 1.0, None, True, False)
             layers.append(dict(s=s, cur_op=cur_op, cur_k=cur_k, hout=hout, mean=mean, rstd=rstd))
@@ -471,13 +499,15 @@ def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, tra
 
 
 def gcn_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: Precision, grads: Dict[str, Tensor],
-                 pfx: str = "gnn.", want_dx: bool = False) -> Optional[Tensor]:
+                 pfx: str = "gnn.", want_dx: bool = False, comm: Comm = SINGLE) -> Optional[Tensor]:
     nl = cfg["gcn_num_layers"]
     n, p, seed, training = tape["n"], tape["p"], tape["seed"], tape["training"]
     dev = dout.device
     use_bn = bool(cfg["gcn_use_bn"])
     dinv = graph.dinv
     rowptr_t, col_t = graph.transpose()
+    red = comm.allreduce_ if comm.active else None
+    nstat = comm.n_global if comm.active else 0
     gs = tape["gw"] if tape["mixed"] else 1.0
     dcur = dout
     dx = None
@@ -493,13 +523,14 @@ def gcn_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: Pre
             name = f"{pfx}bns.{i}."
             dzs, sums, colsum = K.bn_bwd(dcur, None, None, L["s"], L.get("mean"), L.get("rstd"), P.get(name + "weight"),
                                          P.get(name + "bias"), zb, use_bn, True, training, p, seed + 503 + i, gs,
-                                         want_dz_colsum=zb is not None, out_row_scale=dinv)
+                                         want_dz_colsum=zb is not None, out_row_scale=dinv, reduce_fn=red, stat_rows=nstat)
             if use_bn and training:
                 grads[name + "bias"], grads[name + "weight"] = sums[:hout], sums[hout:]
+                _mark_global(grads, comm, name + "bias", name + "weight")
         gs = 1.0
         if zb is not None:
             grads[f"{pfx}convs.{i}.bias"] = colsum
-        u = K.spmm(rowptr_t, col_t, dinv, dzs)        # = Â^T dz = gradient of (x W^T)
+        u = K.spmm(rowptr_t, col_t, dinv, comm.allgather_rows(dzs))        # = Â^T dz = gradient of (x W^T)
         u_op = K.as_operand(u, prec.planes)
         wname = f"{pfx}convs.{i}.lin.weight"
         dw = torch.empty((hout, L["cur_k"]), dtype=torch.float32, device=dev)

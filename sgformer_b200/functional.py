@@ -12,6 +12,7 @@ from torch.autograd import Function
 
 from . import engine as E
 from . import kernels as K
+from .dist import SINGLE, Comm
 from .graph import Graph
 
 Tensor = torch.Tensor
@@ -60,29 +61,31 @@ class SGFormerFn(Function):
     """Fused encoder: logits = fc(mix(TransConv(x), GNN(x, graph))).  Returns fp32 [N, c]."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, graph: Optional[Graph], cfg: dict, prec: E.Precision, training: bool, names, *params):
+    def forward(ctx, x: Tensor, graph: Optional[Graph], cfg: dict, prec: E.Precision, training: bool, comm: Comm, names,
+                *params):
+        """x: the rows this rank owns ([N, d_in], or its [N/P, d_in] block when `comm` is a row-sharding Comm)."""
         P = _pdict(names, params)
         need_tape = any(ctx.needs_input_grad)
         xin = E.input_operand(x, prec)
         seed = E.next_seed()
         tt, tg, th = (E.Tape(), E.Tape(), E.Tape()) if need_tape else (None, None, None)
-        x1 = E.trans_forward(P, cfg, xin, prec, training, seed, tt)
+        x1 = E.trans_forward(P, cfg, xin, prec, training, seed, tt, comm=comm)
         gw = float(cfg["graph_weight"])
         if cfg["use_graph"]:
             add = cfg["aggregate"] == "add"
             fwd = E.gcn_forward if cfg["variant"] == "medium" else E.gconv_forward
-            x2 = fwd(P, cfg, xin, graph, prec, training, seed, tg, mix=x1 if add else None, gw=gw)
+            x2 = fwd(P, cfg, xin, graph, prec, training, seed, tg, mix=x1 if add else None, gw=gw, comm=comm)
             feats = [x2] if add else [x1, x2]
         else:
             feats = [x1]
         logits = E.head_forward(P, cfg, feats, prec, th)
         if need_tape:
-            ctx.state = (cfg, prec, graph, names, params, tt, tg, th, x.requires_grad)
+            ctx.state = (cfg, prec, graph, comm, names, params, tt, tg, th, x.requires_grad)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits: Tensor):
-        cfg, prec, graph, names, params, tt, tg, th, want_dx = ctx.state
+        cfg, prec, graph, comm, names, params, tt, tg, th, want_dx = ctx.state
         P = _pdict(names, params)
         grads: Dict[str, Tensor] = {}
         dfeats = E.head_backward(P, cfg, th, dlogits, prec, grads)
@@ -92,17 +95,21 @@ class SGFormerFn(Function):
             bwd = E.gcn_backward if cfg["variant"] == "medium" else E.gconv_backward
             if cfg["aggregate"] == "add":
                 dm = dfeats[0]
-                dxg = bwd(P, cfg, tg, graph, dm, prec, grads, want_dx=want_dx)
-                dxt = E.trans_backward(P, cfg, tt, dm, 1.0 - gw, prec, grads, want_dx=want_dx)
+                dxg = bwd(P, cfg, tg, graph, dm, prec, grads, want_dx=want_dx, comm=comm)
+                dxt = E.trans_backward(P, cfg, tt, dm, 1.0 - gw, prec, grads, want_dx=want_dx, comm=comm)
             else:
-                dxg = bwd(P, cfg, tg, graph, dfeats[1], prec, grads, want_dx=want_dx)
-                dxt = E.trans_backward(P, cfg, tt, dfeats[0], 1.0, prec, grads, want_dx=want_dx)
+                dxg = bwd(P, cfg, tg, graph, dfeats[1], prec, grads, want_dx=want_dx, comm=comm)
+                dxt = E.trans_backward(P, cfg, tt, dfeats[0], 1.0, prec, grads, want_dx=want_dx, comm=comm)
             if want_dx:
                 dx = K.axpby(dxt, dxg, 1.0, 1.0)
         else:
-            dx = E.trans_backward(P, cfg, tt, dfeats[0], 1.0, prec, grads, want_dx=want_dx)
+            dx = E.trans_backward(P, cfg, tt, dfeats[0], 1.0, prec, grads, want_dx=want_dx, comm=comm)
+        if comm.active:
+            # C5: every parameter gradient is a sum over rows -> one flattened all-reduce over the shards
+            done = grads.get("__global__", ())
+            comm.allreduce_(*[grads[n_] for n_ in names if n_ in grads and n_ not in done])
         ctx.state = None
-        return (dx, None, None, None, None, None, *_grad_list(names, params, grads))
+        return (dx, None, None, None, None, None, None, *_grad_list(names, params, grads))
 
 
 class TransConvFn(Function):

@@ -29,16 +29,18 @@ def _is_symmetric(edge_index: Tensor, n: int) -> bool:
 
 
 class Graph:
-    """rowptr int64 [n+1], col int32 [nnz] (rows = edge targets, sorted columns, duplicates kept), dinv fp32 [n].
-    self_loop_mode 0: large/100M GraphConv; 1: PyG gcn_norm (medium GCN)."""
+    """rowptr int64 [n_rows+1], col int32 [nnz] (rows = edge targets, sorted columns, duplicates kept), dinv fp32 [n_rows].
+    self_loop_mode 0: large/100M GraphConv; 1: PyG gcn_norm (medium GCN).
+    `rows=(r0, r1)`: row shard of the global pattern (column ids stay global) for row-sharded multi-GPU runs."""
 
-    def __init__(self, edge_index: Tensor, n: int, self_loop_mode: int = 0):
+    def __init__(self, edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None):
         if not edge_index.is_cuda:
             raise RuntimeError("Graph needs a CUDA edge_index (no CPU fallback)")
         self.n = int(n)
+        self.rows = rows
         self.self_loop_mode = self_loop_mode
         self.edge_index = edge_index
-        self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True)
+        self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True, rows=rows)
         self._t: Optional[Tuple[Tensor, Tensor]] = None
 
     @property
@@ -50,9 +52,9 @@ class Graph:
         list is symmetric (the usual case after to_undirected)."""
         if self._t is None:
             if _is_symmetric(self.edge_index, self.n):
-                self._t = (self.rowptr, self.col)
+                self._t = (self.rowptr, self.col)      # also true per row shard: rows r0..r1 of A^T == rows of A
             else:
-                rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False)
+                rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)
                 self._t = (rp, cl)
         return self._t
 
@@ -61,15 +63,15 @@ _CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
 _CACHE_MAX = 4
 
 
-def get_graph(edge_index: Tensor, n: int, self_loop_mode: int = 0) -> Graph:
+def get_graph(edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None) -> Graph:
     """Cached Graph for this edge_index tensor (identity: storage pointer, shape, version)."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index, int(n),
-           self_loop_mode)
+           self_loop_mode, rows)
     g = _CACHE.get(key)
     if g is not None and g.edge_index is edge_index:
         _CACHE.move_to_end(key)
         return g
-    g = Graph(edge_index, n, self_loop_mode)
+    g = Graph(edge_index, n, self_loop_mode, rows)
     _CACHE[key] = g
     while len(_CACHE) > _CACHE_MAX:
         _CACHE.popitem(last=False)

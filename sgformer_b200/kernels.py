@@ -86,14 +86,18 @@ def new_like(x: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # graph structure
 # ------------------------------------------------------------------------------------------------
-def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mode: int = 0, want_dinv: bool = True):
-    """-> (rowptr int64 [n+1], col int32 [nnz'], dinv fp32 [n] | None).  See sgf_csr_build."""
+def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mode: int = 0, want_dinv: bool = True,
+              rows: Optional[Tuple[int, int]] = None):
+    """-> (rowptr int64 [n_rows+1], col int32 [nnz'], dinv fp32 [n_rows] | None).  See sgf_csr_build(_rect).
+    `rows=(r0, r1)` builds only that row range of the n x n pattern (row shard; column ids stay global)."""
     _use(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise ValueError("edge_index must be int64 [2, nnz]")
     ei = edge_index.contiguous()
     nnz = ei.shape[1]
     dev = ei.device
+    r0, r1 = rows if rows is not None else (0, n)
+    n_cols, n = n, r1 - r0
     cap = nnz + (n if self_loop_mode == 1 else 0)
     rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
     col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
@@ -101,9 +105,9 @@ def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mod
     nbytes = C.c_size_t(0)
     check(lib().sgf_csr_build_ws_bytes(nnz, n, C.byref(nbytes)), "sgf_csr_build_ws_bytes")
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    check(lib().sgf_csr_build(_p(ei), nnz, n, int(by_source), self_loop_mode, _p(rowptr), _p(col), _p(dinv), _p(ws),
-                              nbytes.value, _stream()), "sgf_csr_build")
-    if self_loop_mode == 1:
+    check(lib().sgf_csr_build_rect(_p(ei), nnz, r0, r1, n_cols, int(by_source), self_loop_mode, _p(rowptr), _p(col),
+                                   _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_build_rect")
+    if self_loop_mode == 1 or rows is not None:
         total = int(rowptr[n].item())
         col = col[:total]
     else:
@@ -388,23 +392,24 @@ def bn_fwd(z: Tensor, res: Optional[Tensor], mix: Optional[Tensor], mean, rstd, 
 def bn_bwd(dy: Optional[Tensor], dy2: Optional[Tensor], row_scale2: Optional[Tensor], z: Tensor, mean, rstd, gamma, beta,
            zbias, use_bn: bool, use_relu: bool, training: bool, p: float, seed: int, gscale: float,
            dres: Optional[Tensor] = None, dres_accumulate: bool = False, want_dz_colsum: bool = False,
-           out_row_scale: Optional[Tensor] = None):
-    """-> (dz, sums [2h] or None (dbeta, dgamma), dz_colsum [h] or None)."""
+           out_row_scale: Optional[Tensor] = None, reduce_fn=None, stat_rows: int = 0):
+    """-> (dz, sums [2h] or None (dbeta, dgamma), dz_colsum [h] or None).
+    `reduce_fn(sums)` runs between the two phases (the row-sharded all-reduce of the BatchNorm sums); `stat_rows` is then
+    the global row count."""
     _use(z)
     rows, h, ld = _mat(z, "z")
     dz = new_like(z)
     _same_ld(ld, dy, dy2, dz, dres)
     sums = None
     if use_bn and training:
-        sums = torch.zeros(2 * h, dtype=torch.float32, device=z.device)
-        check(lib().sgf_bn_bwd_reduce(_p(dy), _p(dy2), _p(row_scale2), _p(z), ld, rows, h, dcode(z), _p(mean), _p(rstd),
-                                      _p(gamma), _p(beta), _p(zbias), int(use_bn), int(use_relu), p, seed, gscale,
-                                      _p(sums), _stream()), "sgf_bn_bwd_reduce")
+        sums = bn_bwd_sums(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, use_relu, p, seed, gscale)
+        if reduce_fn is not None:
+            reduce_fn(sums)
     colsum = torch.zeros(h, dtype=torch.float32, device=z.device) if want_dz_colsum else None
     check(lib().sgf_bn_bwd_apply(_p(dy), _p(dy2), _p(row_scale2), _p(z), ld, rows, h, dcode(z), _p(mean), _p(rstd),
                                  _p(gamma), _p(beta), _p(zbias), int(use_bn), int(use_relu), int(training), p, seed,
-                                 gscale, _p(sums), _p(dz), _p(dres), int(dres_accumulate), _p(colsum), _p(out_row_scale),
-                                 _stream()), "sgf_bn_bwd_apply")
+                                 gscale, int(stat_rows), _p(sums), _p(dz), _p(dres), int(dres_accumulate), _p(colsum),
+                                 _p(out_row_scale), _stream()), "sgf_bn_bwd_apply")
     return dz, sums, colsum
 
 

@@ -7,6 +7,7 @@ import torch.nn.functional as F
 from . import engine as E
 from . import functional as Fn
 from .config import make_config
+from .dist import SINGLE
 from .graph import get_graph
 from .modules import GraphConvBase, GraphConvLayerBase, SGFormerBase, TransConvBase, TransConvLayerBase
 
@@ -95,12 +96,19 @@ class SGFormer(SGFormerBase):
         if not x.is_cuda:
             def run(dev, xd, eid):
                 graph = get_graph(eid, xd.shape[0], 0) if self.use_graph else None
-                return Fn.SGFormerFn.apply(xd, graph, self._cfg(), E.precision(self.precision), self.training, names,
+                return Fn.SGFormerFn.apply(xd, graph, self._cfg(), E.precision(self.precision), self.training, SINGLE, names,
                                            *[t.to(dev) for t in tensors])
             with torch.no_grad():
                 return self._host_call(run, x, edge_index)
-        graph = get_graph(edge_index, x.shape[0], 0) if self.use_graph else None
-        return Fn.SGFormerFn.apply(x, graph, self._cfg(), E.precision(self.precision), self.training, names, *tensors)
+        comm = self._comm
+        if comm.active:
+            # row-sharded: x holds this rank's row block, edge_index is the GLOBAL edge list
+            if x.shape[0] != comm.rows[1] - comm.rows[0]:
+                raise ValueError(f"row-sharded forward expects the {comm.rows[1] - comm.rows[0]} rows of this rank, got {x.shape[0]}")
+            graph = get_graph(edge_index, comm.n_global, 0, rows=comm.rows) if self.use_graph else None
+        else:
+            graph = get_graph(edge_index, x.shape[0], 0) if self.use_graph else None
+        return Fn.SGFormerFn.apply(x, graph, self._cfg(), E.precision(self.precision), self.training, comm, names, *tensors)
 
     def reset_parameters(self):
         # the reference never re-initialises self.fc (large/ours.py:283-286); kept.

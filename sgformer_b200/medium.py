@@ -9,6 +9,7 @@ import torch.nn.functional as F
 from . import engine as E
 from . import functional as Fn
 from .config import make_config
+from .dist import SINGLE
 from .graph import get_graph
 from .modules import SGFormerBase, TransConvBase, TransConvLayerBase, _Base, full_attention_conv
 
@@ -187,12 +188,13 @@ class SGFormer(SGFormerBase):
         names = list(tn) + ["fc." + k for k in fn]
         tensors = list(tt) + ft
         if not self.use_graph:
-            return Fn.SGFormerFn.apply(x, None, self._cfg(), prec, self.training, tuple(names), *tensors)
+            return Fn.SGFormerFn.apply(x, None, self._cfg(), prec, self.training, self._comm, tuple(names), *tensors)
         if fused:
             gn, gt = _gcn_flat(self.gnn, "gnn.")
             cfg = self._cfg(len(self.gnn.convs), float(self.gnn.dropout), bool(self.gnn.use_bn))
-            graph = get_graph(edge_index, x.shape[0], 1)
-            return Fn.SGFormerFn.apply(x, graph, cfg, prec, self.training, tuple(names) + tuple(gn), *tensors, *gt)
+            comm = self._comm
+            graph = get_graph(edge_index, comm.n_global, 1, rows=comm.rows) if comm.active else get_graph(edge_index, x.shape[0], 1)
+            return Fn.SGFormerFn.apply(x, graph, cfg, prec, self.training, comm, tuple(names) + tuple(gn), *tensors, *gt)
         # foreign GNN module: run it as given, mix + fc on the GPU kernels
         x1 = Fn.TransConvFn.apply(x, self.trans_conv._cfg(), prec, self.training, tn, *tt)
         x2 = self.gnn(data)

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from . import engine as E
 from . import functional as Fn
 from .config import make_config
+from .dist import SINGLE
 from .graph import get_graph
 
 Tensor = torch.Tensor
@@ -258,6 +259,14 @@ class GraphConvBase(_Base):
 # =================================================================================================
 class SGFormerBase(_Base):
     variant = "large"
+    _comm = SINGLE
+
+    def set_row_sharding(self, comm):
+        """Row-sharded multi-GPU execution: `comm = sgformer_b200.dist.Comm(group, n_global)`.  forward then
+        takes this rank's row block of x and the global edge_index and returns this rank's rows of the logits; parameter
+        gradients come back already all-reduced.  `None` / `Comm(None)` restores single-GPU execution."""
+        self._comm = comm if comm is not None else SINGLE
+        return self
 
     def _finish_init(self, hidden_channels, out_channels, aggregate):
         if aggregate == "add":

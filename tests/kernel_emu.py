@@ -43,15 +43,22 @@ class Operand:
     planes: int
 
 
-def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True):
+def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True, rows=None):
     src, dst = edge_index[0], edge_index[1]
     if self_loop_mode == 1:
         keep = src != dst
         ar = torch.arange(n)
         src, dst = torch.cat([src[keep], ar]), torch.cat([dst[keep], ar])
     key, val = (src, dst) if by_source else (dst, src)
+    if rows is not None:
+        m = (key >= rows[0]) & (key < rows[1])
+        key, val = key[m] - rows[0], val[m]
+        nr = rows[1] - rows[0]
+    else:
+        nr = n
     order = torch.argsort(key * n + val, stable=True)
-    deg = torch.bincount(key, minlength=n)
+    deg = torch.bincount(key, minlength=nr)
+    n = nr
     rowptr = torch.zeros(n + 1, dtype=torch.int64)
     rowptr[1:] = torch.cumsum(deg, 0)
     d = deg.float()
@@ -227,7 +234,7 @@ def bn_bwd_sums(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, 
 
 
 def bn_bwd(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, use_relu, training, p, seed, gscale, dres=None,
-           dres_accumulate=False, want_dz_colsum=False, out_row_scale=None):
+           dres_accumulate=False, want_dz_colsum=False, out_row_scale=None, reduce_fn=None, stat_rows=0):
     graw = _bn_g(dy, dy2, row_scale2, gscale)
     if dres is not None:
         _st(dres, graw + (dres.float() if dres_accumulate else 0.0))
@@ -236,7 +243,9 @@ def bn_bwd(dy, dy2, row_scale2, z, mean, rstd, gamma, beta, zbias, use_bn, use_r
     sums = None
     if use_bn and training:
         sums = torch.cat([g.sum(0), (g * xh).sum(0)])
-        n = z.shape[0]
+        if reduce_fn is not None:
+            reduce_fn(sums)
+        n = stat_rows if stat_rows > 0 else z.shape[0]
         d = gamma * rstd * (g - sums[:z.shape[1]] / n - xh * sums[z.shape[1]:] / n)
     elif use_bn:
         d = gamma * rstd * g
@@ -306,10 +315,10 @@ def launch_count():
 
 
 class EmuGraph:
-    def __init__(self, edge_index, n, self_loop_mode=0):
-        self.n, self.edge_index, self.self_loop_mode = n, edge_index, self_loop_mode
-        self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True)
+    def __init__(self, edge_index, n, self_loop_mode=0, rows=None):
+        self.n, self.edge_index, self.self_loop_mode, self.rows = n, edge_index, self_loop_mode, rows
+        self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True, rows=rows)
 
     def transpose(self):
-        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False)
+        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)
         return rp, cl

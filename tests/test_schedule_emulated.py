@@ -11,6 +11,7 @@ import kernel_emu
 from sgformer_b200 import engine as E
 from sgformer_b200 import functional as Fn
 from sgformer_b200.config import make_config
+from sgformer_b200.dist import SINGLE
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODEL_FILES = sorted(glob.glob(os.path.join(GOLD, "model_*.pt")))
@@ -45,13 +46,13 @@ def test_fused_schedule_fp32(path):
     n = fx["x"].shape[0]
     graph = kernel_emu.EmuGraph(fx["edge_index"], n, 1 if cfg["variant"] == "medium" else 0)
 
-    out = Fn.SGFormerFn.apply(fx["x"], graph, cfg, E.FP32, False, names, *[sd[k] for k in names])
+    out = Fn.SGFormerFn.apply(fx["x"], graph, cfg, E.FP32, False, SINGLE, names, *[sd[k] for k in names])
     _close(out, fx["out_eval"], 2e-5, 2e-6, "eval output")
 
     params = [sd[k].clone().requires_grad_(True) if (sd[k].is_floating_point() and "running" not in k) else sd[k].clone()
               for k in names]
     x = fx["x"].clone().requires_grad_(True)
-    out = Fn.SGFormerFn.apply(x, graph, cfg, E.FP32, True, names, *params)
+    out = Fn.SGFormerFn.apply(x, graph, cfg, E.FP32, True, SINGLE, names, *params)
     _close(out, fx["out_train"], 2e-5, 2e-6, "train output")
     (out * fx["loss_weight"]).sum().backward()
     _close(x.grad, fx["grad_x"], 5e-4, 2e-6, "grad x")
@@ -80,5 +81,5 @@ def test_bf16_schedule_is_close():
     sd = fx["state_dict"]
     names = tuple(sd.keys())
     graph = kernel_emu.EmuGraph(fx["edge_index"], fx["x"].shape[0], 0)
-    out = Fn.SGFormerFn.apply(fx["x"], graph, cfg, E.BF16, False, names, *[sd[k].clone() for k in names])
+    out = Fn.SGFormerFn.apply(fx["x"], graph, cfg, E.BF16, False, SINGLE, names, *[sd[k].clone() for k in names])
     _close(out, fx["out_eval"], 3e-2, 3e-2, "bf16 eval output")
