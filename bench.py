@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=60000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "rows"],
+                    help="N>1: 'dp' = rank-local graph partitions + gradient all-reduce (weak scaling); 'rows' = ONE graph, "
+                         "nodes row-sharded, K^T V / BN all-reduces + SpMM operand all-gather (strong scaling)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.precision:
@@ -199,16 +202,30 @@ def main():
     from sgformer_b200 import kernels as K
     from sgformer_b200 import large as L
     from sgformer_b200.graph import get_graph
+    from sgformer_b200.loss import nll_loss_from_logits
     from sgformer_b200.synth import make_graph
 
     torch.manual_seed(1234)
     n, d, c, h = w["n"], w["d"], w["c"], w["h"]
-    # rank-local graph partition of the named shape (same shape on every rank, different seed): weak scaling
-    ei = make_graph(n, w["e"], seed=100 + rank, device=dev)
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
-    x = torch.randn(n, d, generator=g, device=dev)
-    y = torch.randint(0, c, (n,), generator=g, device=dev)
+    rows_mode = world > 1 and args.parallel == "rows"
+    if rows_mode:
+        # one global graph (same seed everywhere); every rank keeps its row block of x / y and builds its CSR row shard
+        from sgformer_b200.dist import Comm
+        comm = Comm(dist.group.WORLD, n)
+        r0, r1 = comm.rows
+        ei = make_graph(n, w["e"], seed=100, device=dev)
+        g = torch.Generator(device=dev).manual_seed(7)
+        x = torch.randn(n, d, generator=g, device=dev)[r0:r1].contiguous()
+        y = torch.randint(0, c, (n,), generator=g, device=dev)[r0:r1].contiguous()
+    else:
+        # rank-local graph partition of the named shape (same shape on every rank, different seed): weak scaling
+        ei = make_graph(n, w["e"], seed=100 + rank, device=dev)
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        x = torch.randn(n, d, generator=g, device=dev)
+        y = torch.randint(0, c, (n,), generator=g, device=dev)
     model = L.SGFormer(d, h, c, **model_kwargs(w)).to(dev).set_precision(w["precision"])
+    if rows_mode:
+        model.set_row_sharding(comm)
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
@@ -218,7 +235,7 @@ def main():
     params = [p for p in model.parameters()]
 
     def allreduce_grads():
-        if world == 1:
+        if world == 1 or rows_mode:      # row-sharded: the backward already all-reduces the gradients (C5)
             return
         flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
         dist.all_reduce(flat)
@@ -233,7 +250,7 @@ def main():
     def step(xd, eid, yd):
         opt.zero_grad(set_to_none=True)
         out = model(xd, eid)
-        loss = torch.nn.functional.nll_loss(torch.log_softmax(out, dim=1), yd)
+        loss = nll_loss_from_logits(out, yd, None, float(n))   # mean over the (global) node count; fused fwd+grad kernel
         loss.backward()
         allreduce_grads()
         opt.step()
@@ -258,7 +275,7 @@ def main():
 
     for _ in range(args.warmup):
         step(x, ei, y)
-    graph = get_graph(ei, n, 0)
+    graph = get_graph(ei, n, 0, rows=comm.rows) if rows_mode else get_graph(ei, n, 0)
     nnz = graph.nnz
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -271,7 +288,8 @@ def main():
     K.spmm_events = None
     clocks = sampler.stop() if sampler else None
     spmm_ms = [a.elapsed_time(b) for a, b in ev]
-    value = n * world / (ms_step * 1e-3)
+    total_nodes = n if rows_mode else n * world
+    value = total_nodes / (ms_step * 1e-3)
 
     # end to end: inputs come from pinned host memory every step, loss is read back
     e2e = None
@@ -285,7 +303,7 @@ def main():
 
         e2e_step()
         ms_e2e = timed(e2e_step, max(2, min(args.steps, 5)))
-        e2e = {"value": n * world / (ms_e2e * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+        e2e = {"value": total_nodes / (ms_e2e * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e}
 
     if rank != 0:
@@ -293,7 +311,7 @@ def main():
             dist.destroy_process_group()
         return
     b = 2 if w["precision"] == "bf16" else 4
-    alg = spmm_algorithmic_bytes(n, nnz, h, b)
+    alg = spmm_algorithmic_bytes(graph.rowptr.numel() - 1, nnz, h, b)
     peak, peak_src = peaks()
     roof = None
     if spmm_ms:
@@ -313,14 +331,17 @@ def main():
         cpu = cpu_reference(w, budget_nodes=args.ref_nodes)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": "nodes/sec fwd+bwd", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None,
             "dtype": w["precision"], "data": "synthetic",
             "config": {"workload": f"ogbn-{args.workload}-shaped synthetic, full batch" if args.workload != "papers-batch"
                        else "papers100M-shaped mini-batch (400k nodes)", "nodes_per_gpu": n, "nnz_per_gpu": nnz,
                        "in_features": d, "hidden": h, "classes": c, "gnn_layers": w["layers"], "gnn_use_init": w["use_init"],
                        "attn_layers": 1, "parallelism": "single GPU" if world == 1 else
-                       f"dp{world}: rank-local graph partitions, replicated model, NCCL grad allreduce",
-                       "step": "zero_grad + forward + log_softmax/NLL + backward + fused Adam",
+                       (f"rows{world}: one graph, nodes row-sharded; NCCL all-reduce of K^T V/K^T 1/norms + BN sums + grads, "
+                        f"all-gather of the SpMM operand rows" if rows_mode else
+                        f"dp{world}: rank-local graph partitions, replicated model, NCCL grad allreduce"),
+                       "step": "zero_grad + forward + fused log_softmax/NLL (sgf_softmax_nll) + backward + fused Adam",
                        "l2": "inputs (>= 1 GB of activations per pass) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -203,6 +203,14 @@ int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, int cols, i
 int sgf_head_mean(const void* x, int64_t ldx, int64_t rows, int heads, int d, int dtype, void* out, int64_t ldo,
                   void* stream);
 
+/* Fused log_softmax + NLL over the selected rows, forward value and logits gradient in one pass (replaces
+ * F.log_softmax + nn.NLLLoss on out[train_mask] and their autograd, large/main.py:139-141):
+ *   *loss += scale * sum_{r: mask[r]} -log_softmax(logits[r])[labels[r]]      (caller-zeroed; scale = 1/#selected for 'mean')
+ *   dlogits[r,:] = scale * (softmax(logits[r]) - onehot(labels[r])) for selected rows, 0 otherwise (dlogits nullable).
+ * mask: uint8 [rows] or NULL (all rows). */
+int sgf_softmax_nll(const float* logits, int64_t ld, const int64_t* labels, const uint8_t* mask, int64_t rows, int c,
+                    float scale, float* loss, float* dlogits, int64_t ld_d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Linear attention glue (full_attention_conv, medium/ours.py:14-34; backward per SURVEY.md Appendix A.1)
  * ------------------------------------------------------------------------------------------------ */

@@ -739,6 +739,38 @@ __global__ void attn_prepare_bwd_kernel(const float* __restrict__ s_raw, const f
     }
 }
 
+// fused log_softmax + NLL (mean over `denom` rows) forward AND gradient in one pass over the logits:
+//   loss += -scale * log_softmax(x[r])[y[r]]   and   dlogits[r,:] = scale * (softmax(x[r]) - onehot(y[r]))   (0 for masked rows)
+// Replaces F.log_softmax + nn.NLLLoss on out[train_mask] (reference large/main.py:139-141) and their backward.
+__global__ void __launch_bounds__(kRowBlock) softmax_nll_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ y,
+                                                                 const uint8_t* __restrict__ mask, int64_t rows, int c, float scale,
+                                                                 float* __restrict__ loss, float* __restrict__ dx, int64_t lddx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float acc = 0.f;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const bool on = mask ? mask[r] != 0 : true;
+        const float* xr = x + r * ldx;
+        float m = -INFINITY;
+        for (int j = lane; j < c; j += 32) m = fmaxf(m, xr[j]);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float se = 0.f;
+        for (int j = lane; j < c; j += 32) se += __expf(xr[j] - m);
+        se = warp_sum(se);
+        const float lse = m + __logf(se);
+        const int64_t lab = y[r];
+        if (on && lane == 0 && lab >= 0 && lab < c) acc += lse - xr[lab];
+        if (dx) {
+            float* dr = dx + r * lddx;
+            const float s = on ? scale : 0.f;
+            for (int j = lane; j < c; j += 32) dr[j] = s * (__expf(xr[j] - lse) - (j == lab ? 1.f : 0.f));
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && acc != 0.f) atomicAdd(loss, acc * scale);
+}
+
 }  // namespace sgf
 
 using namespace sgf;
@@ -990,6 +1022,19 @@ extern "C" int sgf_attn_prepare_bwd(const float* s_raw, const float* z_raw, cons
                                                                      (__nv_bfloat16*)b_dq, ld_b_dq, (__nv_bfloat16*)b_dv, ld_b_dv,
                                                                      (__nv_bfloat16*)b_dk, ld_b_dk, plane_ld_d, plane_ld_m, r1_col,
                                                                      dk_bias, scal_bwd);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_softmax_nll(const float* logits, int64_t ld, const int64_t* labels, const uint8_t* mask, int64_t rows, int c,
+                               float scale, float* loss, float* dlogits, int64_t ld_d, void* stream) {
+    if (!logits || !labels || !loss || rows < 0 || c <= 0) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    int64_t blocks = (rows * 32 + kRowBlock - 1) / kRowBlock;
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    softmax_nll_kernel<<<(unsigned)blocks, kRowBlock, 0, (cudaStream_t)stream>>>(logits, ld, labels, mask, rows, c, scale, loss,
+                                                                               dlogits, ld_d);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

@@ -13,6 +13,7 @@ medium/models.py:49-63 (GCN over PyG GCNConv), large/ours.py:265-276 (SGFormer.f
 from __future__ import annotations
 
 import itertools
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -70,13 +71,27 @@ def _w(P: Dict[str, Tensor], name: str, prec: Precision, transpose: bool = False
     return K.pack_operand(P[name], transpose, prec.planes)
 
 
+_xin_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
 def input_operand(x: Tensor, prec: Precision) -> K.Operand:
-    """Raw node features fp32 [N, d_in] -> tensor-core operand (read by both branches' input Linear)."""
-    if x.dtype != torch.float32:
-        x = x.float()
-    if x.stride(-1) != 1:
-        x = x.contiguous()
-    return K.pack_operand(x, False, prec.planes)
+    """Raw node features fp32 [N, d_in] -> tensor-core operand (read by both branches' input Linear).  Full-batch
+    training feeds the same feature tensor every step, so the packed operand is cached on the tensor's identity/version."""
+    key = (x.data_ptr(), tuple(x.shape), x._version, str(x.dtype), prec.name, x.device.index)
+    hit = _xin_cache.get(key)
+    if hit is not None and hit[0] is x:
+        _xin_cache.move_to_end(key)
+        return hit[1]
+    xs = x
+    if xs.dtype != torch.float32:
+        xs = xs.float()
+    if xs.stride(-1) != 1:
+        xs = xs.contiguous()
+    op = K.pack_operand(xs.detach(), False, prec.planes)
+    _xin_cache[key] = (x, op)
+    while len(_xin_cache) > 2:
+        _xin_cache.popitem(last=False)
+    return op
 
 
 # =================================================================================================

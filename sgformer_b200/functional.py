@@ -266,3 +266,19 @@ class SpMMFn(Function):
         dx = K.spmm(rp, cl, graph.dinv, ds)
         ctx.state = None
         return _from_act(dx, dtx), None, None
+
+
+class SoftmaxNLLFn(Function):
+    """mean NLL of log_softmax(logits) over the selected rows; the logits gradient is produced by the same pass."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mask, denom):
+        loss, d = K.softmax_nll(logits, labels, mask, 1.0 / float(denom), want_grad=ctx.needs_input_grad[0])
+        ctx.d = d
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d
+        ctx.d = None
+        return (d if g is None else d * g), None, None, None

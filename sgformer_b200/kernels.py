@@ -504,5 +504,24 @@ def attn_combine_scal(scal_bwd_all: Tensor, heads: int, scal_fwd: Tensor):
           "sgf_attn_combine_scal")
 
 
+def softmax_nll(logits: Tensor, labels: Tensor, mask: Optional[Tensor], scale: float, want_grad: bool = True):
+    """-> (loss fp32 [1], dlogits fp32 [rows, c] | None).  See sgf_softmax_nll."""
+    _use(logits)
+    if logits.dtype != torch.float32 or labels.dtype != torch.int64:
+        raise TypeError("softmax_nll expects fp32 logits and int64 labels")
+    rows, c, ld = _mat(logits, "logits")
+    labels = labels.reshape(-1).contiguous()
+    if labels.numel() != rows:
+        raise ValueError("labels / logits row mismatch")
+    m = None
+    if mask is not None:
+        m = mask.reshape(-1).to(torch.uint8).contiguous()
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    d = torch.empty((rows, c), dtype=torch.float32, device=logits.device) if want_grad else None
+    check(lib().sgf_softmax_nll(_p(logits), ld, _p(labels), _p(m), rows, c, scale, _p(loss), _p(d), c, _stream()),
+          "sgf_softmax_nll")
+    return loss, d
+
+
 def launch_count() -> int:
     return int(lib().sgf_launch_count())

@@ -310,6 +310,18 @@ def attn_combine_scal(scal_bwd_all, heads, scal_fwd):
     scal_bwd_all[:, 2] = -c * scal_fwd[1] ** 2
 
 
+def softmax_nll(logits, labels, mask, scale, want_grad=True):
+    lp = torch.log_softmax(logits.float(), 1)
+    sel = torch.ones(logits.shape[0], dtype=torch.bool) if mask is None else mask.bool()
+    loss = -(lp[torch.arange(logits.shape[0]), labels] * sel).sum() * scale
+    d = None
+    if want_grad:
+        d = lp.exp()
+        d[torch.arange(logits.shape[0]), labels] -= 1.0
+        d = d * sel[:, None] * scale
+    return loss.reshape(1), d
+
+
 def launch_count():
     return 0
 

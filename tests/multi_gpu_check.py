@@ -1,0 +1,63 @@
+"""torchrun script (not a pytest file): row-sharded execution on N GPUs over NCCL must reproduce the single-GPU result.
+Run by scripts/gpu_multi.sh:  torchrun --nproc-per-node N tests/multi_gpu_check.py"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from sgformer_b200 import large as L
+    from sgformer_b200.dist import Comm
+    from sgformer_b200.synth import make_graph
+    ok = True
+    for prec, tol in (("fp32", 2e-4), ("bf16", 2e-2)):
+        torch.manual_seed(0)
+        n, d, h, c = 30011, 48, 128, 7
+        ei = make_graph(n, 200000, seed=3).to(dev)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(n, d, generator=g).to(dev)
+        y = torch.randint(0, c, (n,), generator=g).to(dev)
+        kw = dict(gnn_num_layers=2, gnn_use_init=True, graph_weight=0.5, gnn_dropout=0.0, trans_dropout=0.0)
+        ref = L.SGFormer(d, h, c, **kw).to(dev).set_precision(prec)
+        for p in ref.parameters():
+            dist.broadcast(p.data, 0)
+        shard = L.SGFormer(d, h, c, **kw).to(dev).set_precision(prec)
+        shard.load_state_dict(ref.state_dict())
+        comm = Comm(dist.group.WORLD, n)
+        shard.set_row_sharding(comm)
+        r0, r1 = comm.rows
+        ref.train(); shard.train()
+        out_ref = ref(x, ei)
+        (torch.nn.functional.nll_loss(torch.log_softmax(out_ref, 1), y, reduction="sum") / n).backward()
+        out = shard(x[r0:r1].contiguous(), ei)
+        (torch.nn.functional.nll_loss(torch.log_softmax(out, 1), y[r0:r1], reduction="sum") / n).backward()
+        err = (out - out_ref[r0:r1]).abs().max().item() / out_ref.abs().max().item()
+        gerr = 0.0
+        for (k, p), (_, q) in zip(shard.named_parameters(), ref.named_parameters()):
+            scale = max(q.grad.abs().max().item(), 1e-6)
+            gerr = max(gerr, (p.grad - q.grad).abs().max().item() / scale) if "bias" not in k else gerr
+        good = err <= tol and gerr <= (2e-2 if prec == "fp32" else 0.3)
+        ok = ok and good
+        if rank == 0:
+            print(f"[{prec}] world={world}: logits rel err {err:.3e}, worst weight-grad rel err {gerr:.3e} -> {'OK' if good else 'FAIL'}")
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if flag.item() != 1:
+        sys.exit(1)
+    if rank == 0:
+        print("multi_gpu_check: OK")
+
+
+if __name__ == "__main__":
+    main()

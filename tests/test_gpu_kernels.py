@@ -255,6 +255,24 @@ def test_dropout_statistics_and_consistency(K):
     assert abs((yb > 0).float().mean().item() - (1 - p)) < 0.01 and torch.equal(dz > 0, yb > 0)
 
 
+def test_softmax_nll_matches_torch(K):
+    from sgformer_b200.loss import nll_loss_from_logits
+    g = torch.Generator().manual_seed(4)
+    for n, c in [(1000, 47), (333, 2), (5000, 172), (64, 7)]:
+        x = (torch.randn(n, c, generator=g) * 3).to(DEV).requires_grad_(True)
+        y = torch.randint(0, c, (n,), generator=g).to(DEV)
+        mask = (torch.rand(n, generator=g) < 0.5).to(DEV)
+        for m in (None, mask):
+            xr = x.detach().clone().requires_grad_(True)
+            ref = torch.nn.functional.nll_loss(torch.log_softmax(xr if m is None else xr[m], 1), y if m is None else y[m])
+            ref.backward()
+            x.grad = None
+            loss = nll_loss_from_logits(x, y, m)
+            (loss * 2.0).backward()
+            _close(loss, ref, 1e-5, 1e-6, f"loss n={n} c={c}")
+            _close(x.grad, 2.0 * xr.grad, 1e-4, 1e-7, "dlogits")
+
+
 def test_pack_operand(K):
     g = torch.Generator().manual_seed(2)
     src = torch.randn(130, 47, generator=g)
