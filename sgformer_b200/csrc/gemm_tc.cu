@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                 tmem_ld_wait();
                 const float den = t[0] + p.nf;
                 inv_den = 1.f / den;
-                if (row_ok && p.den_out && half == 0) p.den_out[row] = den;
+                if (row_ok && p.den_out && half == 0 && n_blk == 0) p.den_out[row] = den;
             }
             const float rs = (p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
             const float r1r = (p.r1_row && row_ok) ? p.r1_row[row] : 0.f;
@@ -555,6 +555,9 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     p.n_out = a->n_out;
     const int n16 = (a->n_out + 15) / 16 * 16;
     p.n_blocks = (n16 + 255) / 256;
+    // a 16-column tail needs n-block + 16 <= 256 TMEM columns per accumulator stage to keep the two stages (MMA of tile i+1
+    // overlapping the epilogue of tile i): split a 256-wide output into two 128(+16) blocks (the tail is recomputed, cheap)
+    if (has_tail && n16 + 16 > 256) p.n_blocks = 2;
     // equal-width n-blocks, each a multiple of 16
     p.bn_main = ((n16 / 16 + p.n_blocks - 1) / p.n_blocks) * 16;
     p.has_tail = has_tail ? 1 : 0;
