@@ -31,6 +31,10 @@ WORKLOADS = {
     "arxiv": dict(n=169343, d=128, e=1166243, c=40, h=256, layers=3, use_init=False, precision="fp32"),
     "pokec": dict(n=1632803, d=65, e=30622564, c=2, h=64, layers=2, use_init=True, precision="bf16"),
     "papers-batch": dict(n=400000, d=128, e=430000, c=172, h=256, layers=3, use_init=True, precision="bf16"),
+    # ogbn-papers100M-shaped, one GPU's shard of an 8-way node partition (111 M / 8 nodes; 1/8 of a node's ~29.7 neighbours are
+    # in the same shard), trained with the random-partition mini-batches of large/main-batch.py (batch 400 k, slides / run.sh)
+    "papers100M-minibatch": dict(n=13882494, d=128, e=25700000, c=172, h=256, layers=3, use_init=True, precision="bf16",
+                                 batch=400000),
     "tiny": dict(n=20000, d=64, e=200000, c=7, h=64, layers=2, use_init=True, precision="bf16"),
 }
 
@@ -257,7 +261,7 @@ def main():
         opt.step()
         return loss
 
-    def timed(fn, steps):
+    def timed(fn, steps):  # noqa: E306
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -273,6 +277,54 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
+
+    minibatch = "batch" in w
+    if minibatch:
+        # mini-batch path (large/main-batch.py:130-151) kept on the device: CSR built once, per step a random batch ->
+        # Graph.subset (K9 on the CSR) -> feature gather -> fwd/bwd -> (grad all-reduce) -> Adam
+        from sgformer_b200.graph import Graph
+        from sgformer_b200.minibatch import RandomPartitionSampler
+        full = Graph(ei, n)
+        bsz = w["batch"]
+        cap = int(bsz * (2.0 * w["e"] / n * bsz / n + 1.0) * 1.5) + 1024     # induced nnz bound: no per-batch device sync
+        sampler = RandomPartitionSampler(full, x, y, bsz, capacity=cap,
+                                         generator=torch.Generator(device=dev).manual_seed(11 + rank))
+        batches = iter(())
+
+        def mb_step():
+            nonlocal batches
+            mb = next(batches, None)
+            if mb is None or mb.idx.numel() < bsz:      # new epoch (skip the ragged last batch: fixed work per step)
+                batches = iter(sampler)
+                mb = next(batches)
+            opt.zero_grad(set_to_none=True)
+            loss = nll_loss_from_logits(model(mb), mb.labels, None, float(bsz))
+            loss.backward()
+            allreduce_grads()
+            opt.step()
+            return loss
+
+        for _ in range(args.warmup):
+            mb_step()
+        l0 = K.launch_count()
+        ms_step = timed(mb_step, args.steps)
+        launches = K.launch_count() - l0
+        if rank == 0:
+            line = {"metric": "nodes/sec fwd+bwd", "value": bsz * world / (ms_step * 1e-3), "unit": "nodes/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": w["precision"], "data": "synthetic",
+                    "config": {"workload": "ogbn-papers100M-shaped, random-partition mini-batches (large/main-batch.py)",
+                               "batch_nodes_per_gpu": bsz, "shard_nodes_per_gpu": n, "shard_nnz": full.nnz, "in_features": d,
+                               "hidden": h, "classes": c, "gnn_layers": w["layers"], "gnn_use_init": True,
+                               "parallelism": "single GPU" if world == 1 else
+                               f"dp{world}: rank-local node shards, replicated model, NCCL grad allreduce",
+                               "step": "sample batch + Graph.subset (K9 on CSR) + feature gather + fwd + fused loss + bwd + Adam",
+                               "cuda_graph": False},
+                    "e2e": None, "gpu_launches": launches, "clocks": None, "roofline": None, "cpu_baseline": None}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     for _ in range(args.warmup):
         step(x, ei, y)

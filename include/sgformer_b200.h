@@ -72,6 +72,15 @@ int sgf_subgraph(const int64_t* edge_index, int64_t nnz, int64_t n, const int64_
                  int32_t* node_map, int64_t* out_edge_index /* [2,nnz] capacity, pitch nnz */,
                  int64_t* out_count, void* ws, size_t ws_bytes, void* stream);
 int sgf_subgraph_ws_bytes(int64_t nnz, int64_t n, size_t* bytes);
+/* K9 on the CSR: the induced subgraph of `subset` emitted directly as the subset's own CSR (rows = subset order, columns
+ * = positions in subset, sorted; dinv from the induced in-degrees) — the structure GraphConv needs for a mini-batch, in
+ * O(sum of the subset rows' lengths) instead of PyG subgraph's O(E) mask per batch + a CSR rebuild.
+ * node_map: int32 [n] scratch that must hold -1 everywhere on entry and is restored to -1 on exit (kept across batches).
+ * out_col_capacity >= sum of the subset rows' lengths is always enough. */
+int sgf_csr_subset_ws_bytes(int64_t n_sub, int64_t max_out_nnz, size_t* bytes);
+int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* subset, int64_t n_sub,
+                   int32_t* node_map, int64_t* out_rowptr /* [n_sub+1] */, int32_t* out_col, int64_t out_col_capacity,
+                   float* dinv /* [n_sub] or NULL */, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K6 / K7 — CSR SpMM (replaces torch_sparse.matmul(adj, x), large/ours.py:34, 100M/ours.py:80, and its
@@ -198,7 +207,9 @@ int sgf_axpby(const void* x, int64_t ldx, int x_dtype, const void* y, int64_t ld
  * src ~= p0 + p1 + p2 (bf16x3 split: fp32-accurate products on the bf16 tensor cores).  colsum (nullable, caller-zeroed):
  * exact fp32 column sums of src (bias gradients). */
 int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, int cols, int transpose, void* dst,
-                     int64_t ld_dst, int kp, int64_t plane_ld, float* colsum, void* stream);
+                     int64_t ld_dst, int kp, int64_t plane_ld, float* colsum,
+                     const int64_t* row_index /* nullable: dst row r = src row row_index[r] (mini-batch feature gather,
+                     large/main-batch.py:138 x[idx_i]); rows = number of gathered rows; not with transpose */, void* stream);
 /* mean over heads: out[r,c] = (1/heads) * sum_h x[r, h*d + c]  (TransConvLayer, medium/ours.py:95) */
 int sgf_head_mean(const void* x, int64_t ldx, int64_t rows, int heads, int d, int dtype, void* out, int64_t ldo,
                   void* stream);

@@ -322,6 +322,52 @@ __global__ void subgraph_scatter_kernel(const int64_t* __restrict__ ei, int64_t 
     }
 }
 
+// ---- K9 on the CSR: induced subgraph of a node subset, emitted directly as the subset's CSR -----------------------------
+// O(sum of the subset rows' lengths) instead of the O(E) mask over all edges of PyG subgraph (large/main-batch.py:139).
+__global__ void subset_unmap_kernel(const int64_t* __restrict__ subset, int64_t n_sub, int64_t n, int32_t* __restrict__ node_map) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sub; i += stride) {
+        int64_t v = subset[i];
+        if (v >= 0 && v < n) node_map[v] = -1;
+    }
+}
+__global__ void subset_count_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                    const int64_t* __restrict__ subset, int64_t n_sub, int64_t n,
+                                    const int32_t* __restrict__ node_map, int* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n_sub; i += nwarps) {
+        const int64_t v = subset[i];
+        int c = 0;
+        if (v >= 0 && v < n)
+            for (int64_t j = rowptr[v] + lane; j < rowptr[v + 1]; j += 32) c += node_map[col[j]] >= 0;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) counts[i] = c;
+    }
+}
+__global__ void subset_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   const int64_t* __restrict__ subset, int64_t n_sub, int64_t n,
+                                   const int32_t* __restrict__ node_map, const int64_t* __restrict__ out_rowptr,
+                                   int32_t* __restrict__ out_col) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n_sub; i += nwarps) {
+        const int64_t v = subset[i];
+        if (v < 0 || v >= n) continue;
+        int64_t w = out_rowptr[i];
+        const int64_t s = rowptr[v], e = rowptr[v + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            const int64_t j = base + lane;
+            const int32_t m = j < e ? node_map[col[j]] : -1;
+            const unsigned keep = __ballot_sync(0xffffffffu, m >= 0);
+            if (m >= 0) out_col[w + __popc(keep & ((1u << lane) - 1u))] = m;
+            w += __popc(keep);
+        }
+    }
+}
+
 static inline int grid_for(int64_t work, int block, int per_sm = 8) {
     int64_t g = (work + block - 1) / block;
     int64_t cap = (int64_t)num_sms() * per_sm;
@@ -492,5 +538,50 @@ extern "C" int sgf_subgraph(const int64_t* edge_index, int64_t nnz, int64_t n, c
     if (rc) return rc;
     subgraph_scatter_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, nnz, node_map, flags, pos, out_edge_index, nnz);
     SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+// workspace: counts int32[n_sub+1] | cursor int32[n_sub+1] | block_sums | misc | long_rows int64[n_sub+1] | sort scratch
+extern "C" int sgf_csr_subset_ws_bytes(int64_t n_sub, int64_t max_out_nnz, size_t* bytes) {
+    if (!bytes || n_sub < 0 || max_out_nnz < 0) return SGF_ERR_ARG;
+    *bytes = carve_ws(nullptr, max_out_nnz, n_sub).bytes;
+    return SGF_OK;
+}
+
+extern "C" int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* subset, int64_t n_sub,
+                              int32_t* node_map, int64_t* out_rowptr, int32_t* out_col, int64_t out_col_capacity, float* dinv,
+                              void* ws, size_t ws_bytes, void* stream) {
+    if (!rowptr || n < 0 || n_sub < 0 || !node_map || !out_rowptr || !ws || (n_sub > 0 && !subset)) return SGF_ERR_ARG;
+    CsrWs w = carve_ws(ws, out_col_capacity, n_sub);
+    if (ws_bytes < w.bytes) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_sub == 0) {
+        SGF_CUDA_TRY(cudaMemsetAsync(out_rowptr, 0, 8, st));
+        return SGF_OK;
+    }
+    SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
+    // node_map holds -1 everywhere on entry (maintained by the caller across batches) and is restored on exit
+    subgraph_map_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(subset, n_sub, n, node_map);
+    SGF_LAUNCH_CHECK(); count_launch();
+    subset_count_kernel<<<grid_for(n_sub * 32, 256), 256, 0, st>>>(rowptr, col, subset, n_sub, n, node_map, w.counts);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int rc = launch_scan(w.counts, n_sub, 0, out_rowptr, w.block_sums, w.total, w.cursor, st);
+    if (rc) return rc;
+    subset_fill_kernel<<<grid_for(n_sub * 32, 256), 256, 0, st>>>(rowptr, col, subset, n_sub, n, node_map, out_rowptr, out_col);
+    SGF_LAUNCH_CHECK(); count_launch();
+    subset_unmap_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(subset, n_sub, n, node_map);
+    SGF_LAUNCH_CHECK(); count_launch();
+    // local ids are a permutation of the global ones: restore sorted rows (canonical CSR)
+    csr_sort_rows_warp_kernel<<<grid_for(n_sub * 32, 256), 256, 0, st>>>(out_rowptr, n_sub, out_col, w.long_rows, w.n_long);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int64_t share = w.scratch_elems / kHubBlocks;
+    csr_sort_rows_block_kernel<<<num_sms() * 4, 256, 0, st>>>(out_rowptr, out_col, w.long_rows, w.n_long, w.scratch, 0, 0, kSortSmemMax);
+    SGF_LAUNCH_CHECK(); count_launch();
+    csr_sort_rows_block_kernel<<<kHubBlocks, 1024, 0, st>>>(out_rowptr, out_col, w.long_rows, w.n_long, w.scratch, share, kSortSmemMax, share);
+    SGF_LAUNCH_CHECK(); count_launch();
+    if (dinv) {
+        csr_dinv_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(out_rowptr, n_sub, dinv);
+        SGF_LAUNCH_CHECK(); count_launch();
+    }
     return SGF_OK;
 }

@@ -553,7 +553,8 @@ __global__ void __launch_bounds__(kRowBlock) axpby_kernel(const TI* __restrict__
 // Optional exact fp32 column sums of the source (bias gradients).
 __global__ void __launch_bounds__(kRowBlock) pack_operand_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
                                                                   int transpose, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
-                                                                  int kp, int64_t plane_ld, float* __restrict__ colsum) {
+                                                                  int kp, int64_t plane_ld, float* __restrict__ colsum,
+                                                                  const int64_t* __restrict__ row_index) {
     extern __shared__ float sm[];
     const int64_t rows_out = transpose ? cols : rows;
     const int cols_out = transpose ? (int)rows : cols;
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(kRowBlock) pack_operand_kernel(const float* __
         const int c = (int)(t - r * kp);
         float v = 0.f;
         if (c < cols_out) {
-            v = transpose ? src[(int64_t)c * ld_src + r] : src[r * ld_src + c];
+            v = transpose ? src[(int64_t)c * ld_src + r] : src[(row_index ? row_index[r] : r) * ld_src + c];
             if (colsum) atomicAdd(&sm[transpose ? (int)r : c], v);
         }
         __nv_bfloat16 p0 = __float2bfloat16_rn(v);
@@ -956,14 +957,14 @@ extern "C" int sgf_axpby(const void* x, int64_t ldx, int x_dtype, const void* y,
 }
 
 extern "C" int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, int cols, int transpose, void* dst,
-                                int64_t ld_dst, int kp, int64_t plane_ld, float* colsum, void* stream) {
-    if (!src || !dst || rows <= 0 || cols <= 0 || kp <= 0) return SGF_ERR_ARG;
+                                int64_t ld_dst, int kp, int64_t plane_ld, float* colsum, const int64_t* row_index, void* stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || kp <= 0 || (row_index && transpose)) return SGF_ERR_ARG;
     const int64_t cols_out = transpose ? rows : cols;
     if (kp < cols_out || (plane_ld > 0 && plane_ld < kp) || ld_dst < (plane_ld > 0 ? 2 * plane_ld + kp : kp)) return SGF_ERR_ARG;
     if (colsum && cols > 8192) return SGF_ERR_UNSUPPORTED;
     const int64_t rows_out = transpose ? cols : rows;
     pack_operand_kernel<<<ew_grid(rows_out * kp), kRowBlock, colsum ? cols * sizeof(float) : 0, (cudaStream_t)stream>>>(
-        src, ld_src, rows, cols, transpose, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, colsum);
+        src, ld_src, rows, cols, transpose, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, colsum, row_index);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

@@ -47,6 +47,28 @@ class Graph:
     def nnz(self) -> int:
         return self.col.numel()
 
+    @classmethod
+    def _from_parts(cls, n, rowptr, col, dinv, transpose_same: bool):
+        g = cls.__new__(cls)
+        g.n, g.rows, g.self_loop_mode, g.edge_index = int(n), None, 0, None
+        g.rowptr, g.col, g.dinv = rowptr, col, dinv
+        g._t = (rowptr, col) if transpose_same else None
+        return g
+
+    def subset(self, idx: Tensor, capacity: Optional[int] = None) -> "Graph":
+        """Induced subgraph of the nodes `idx` (int64, local id = position in idx), built from this CSR in
+        O(sum of the selected rows' lengths) — the mini-batch structure of large/main-batch.py:136-139 without the per-batch
+        O(E) PyG `subgraph` mask and without a CSR rebuild.  Requires a symmetric edge set for the backward (checked once)."""
+        if self.rows is not None:
+            raise ValueError("subset() needs the full (unsharded) graph")
+        if not hasattr(self, "_node_map"):
+            self._node_map = torch.full((max(self.n, 1),), -1, dtype=torch.int32, device=self.rowptr.device)
+            self._symmetric = self.transpose()[0] is self.rowptr
+            if not self._symmetric:
+                raise NotImplementedError("Graph.subset: directed graphs need the transposed subset as well")
+        rp, cl, dv = K.csr_subset(self.rowptr, self.col, self.n, idx, self._node_map, capacity)
+        return Graph._from_parts(idx.numel(), rp, cl, dv, True)
+
     def transpose(self) -> Tuple[Tensor, Tensor]:
         """CSR of the transposed pattern (rows = edge sources) for the backward SpMM; shares storage when the edge
         list is symmetric (the usual case after to_undirected)."""

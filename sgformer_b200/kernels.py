@@ -138,6 +138,26 @@ def subgraph(edge_index: Tensor, n: int, subset: Tensor) -> Tensor:
 spmm_events = None
 
 
+def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Tensor, capacity: Optional[int] = None):
+    """Induced-subgraph CSR of `subset` from the full CSR.  -> (rowptr int64 [b+1], col int32 [nnz_b], dinv fp32 [b]).
+    `capacity` bounds the output nnz (default: a device sync to read the exact sum of the subset rows' lengths)."""
+    _use(rowptr)
+    subset = subset.contiguous().to(torch.int64)
+    b = subset.numel()
+    dev = rowptr.device
+    if capacity is None:
+        capacity = int((rowptr[subset + 1] - rowptr[subset]).sum().item()) if b else 0
+    out_rowptr = torch.empty(b + 1, dtype=torch.int64, device=dev)
+    out_col = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    dinv = torch.empty(max(b, 1), dtype=torch.float32, device=dev)
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_csr_subset_ws_bytes(b, capacity, C.byref(nbytes)), "sgf_csr_subset_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    check(lib().sgf_csr_subset(_p(rowptr), _p(col), n, _p(subset), b, _p(node_map), _p(out_rowptr), _p(out_col), capacity,
+                               _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_subset")
+    return out_rowptr, out_col, dinv[:b]
+
+
 def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     _use(x)
     n = rowptr.numel() - 1
@@ -191,17 +211,24 @@ def operand_from_bf16(x: Tensor) -> Operand:
     return Operand(x, rows, k, k, 1)
 
 
-def pack_operand(src: Tensor, transpose: bool = False, planes: int = 1, colsum: Optional[Tensor] = None) -> Operand:
-    """fp32 [r, c] -> bf16 Operand ([c, r] if transpose).  planes=3: bf16x3 split (fp32-accurate products)."""
+def pack_operand(src: Tensor, transpose: bool = False, planes: int = 1, colsum: Optional[Tensor] = None,
+                 row_index: Optional[Tensor] = None) -> Operand:
+    """fp32 [r, c] -> bf16 Operand ([c, r] if transpose).  planes=3: bf16x3 split (fp32-accurate products).
+    row_index (int64 [b]): gather rows src[row_index] while packing (mini-batch features)."""
     _use(src)
     if src.dtype != torch.float32:
         raise TypeError("pack_operand expects fp32")
     r, c, ld = _mat(src, "src")
+    if row_index is not None:
+        if row_index.dtype != torch.int64 or transpose:
+            raise ValueError("row_index must be int64 and cannot be combined with transpose")
+        row_index = row_index.contiguous()
+        r = row_index.numel()
     rows_out, cols_out = (c, r) if transpose else (r, c)
     kp = ceil_to(cols_out, 64) if planes == 3 else ceil_to(cols_out, 8)
     dst = torch.empty((rows_out, kp * planes), dtype=torch.bfloat16, device=src.device)
     check(lib().sgf_pack_operand(_p(src), ld, r, c, int(transpose), _p(dst), dst.stride(0), kp, kp if planes == 3 else 0,
-                                 _p(colsum), _stream()), "sgf_pack_operand")
+                                 _p(colsum), _p(row_index), _stream()), "sgf_pack_operand")
     return Operand(dst, rows_out, cols_out, kp, planes)
 
 

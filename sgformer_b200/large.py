@@ -8,7 +8,8 @@ from . import engine as E
 from . import functional as Fn
 from .config import make_config
 from .dist import SINGLE
-from .graph import get_graph
+from .graph import Graph, get_graph
+from .minibatch import MiniBatch
 from .modules import GraphConvBase, GraphConvLayerBase, SGFormerBase, TransConvBase, TransConvLayerBase
 
 __all__ = ["GraphConvLayer", "GraphConv", "TransConvLayer", "TransConv", "SGFormer"]
@@ -93,6 +94,8 @@ class SGFormer(SGFormerBase):
 
     def forward(self, x, edge_index):
         names, tensors = self._flat()
+        if isinstance(x, MiniBatch):
+            x, edge_index = x.features, x.graph
         if not x.is_cuda:
             def run(dev, xd, eid):
                 graph = get_graph(eid, xd.shape[0], 0) if self.use_graph else None
@@ -106,6 +109,8 @@ class SGFormer(SGFormerBase):
             if x.shape[0] != comm.rows[1] - comm.rows[0]:
                 raise ValueError(f"row-sharded forward expects the {comm.rows[1] - comm.rows[0]} rows of this rank, got {x.shape[0]}")
             graph = get_graph(edge_index, comm.n_global, 0, rows=comm.rows) if self.use_graph else None
+        elif isinstance(edge_index, Graph):
+            graph = edge_index      # a prebuilt structure (e.g. Graph.subset(idx) of a mini-batch) instead of an edge list
         else:
             graph = get_graph(edge_index, x.shape[0], 0) if self.use_graph else None
         return Fn.SGFormerFn.apply(x, graph, self._cfg(), E.precision(self.precision), self.training, comm, names, *tensors)

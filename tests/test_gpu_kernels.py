@@ -124,6 +124,27 @@ def test_subgraph_bit_exact(K):
     assert empty.shape == (2, 0)
 
 
+def test_csr_subset_matches_subgraph_then_build(K):
+    """K9 on the CSR == PyG-semantics subgraph (sgf_subgraph) followed by a CSR build, bit-exactly; node_map is restored."""
+    from sgformer_b200.graph import Graph
+    from sgformer_b200.synth import make_graph
+    n = 20000
+    ei = make_graph(n, 150000, seed=2).to(DEV)
+    full = Graph(ei, n)
+    g = torch.Generator().manual_seed(1)
+    for b in (1, 777, 5000):
+        idx = torch.randperm(n, generator=g)[:b].to(DEV)
+        sub = full.subset(idx)
+        ei_sub = K.subgraph(ei, n, idx)
+        rp, cl, dv = K.csr_build(ei_sub, b)
+        assert torch.equal(sub.rowptr, rp) and torch.equal(sub.col, cl) and torch.equal(sub.dinv, dv)
+        assert int((full._node_map != -1).sum()) == 0
+    x = torch.randn(n, 24, device=DEV)
+    idx = torch.randperm(n, generator=g)[:300].to(DEV)
+    a, b_ = K.pack_operand(x, row_index=idx), K.pack_operand(x[idx].contiguous())
+    assert torch.equal(a.data, b_.data)
+
+
 # ------------------------------------------------------------------------------------------------
 # K6/K7: SpMM
 # ------------------------------------------------------------------------------------------------

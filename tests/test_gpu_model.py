@@ -223,6 +223,32 @@ def test_model_matches_oracle_midsize(n, e, d, h, c, kw, precision, tol):
     assert not problems, "\n".join(problems)
 
 
+def test_minibatch_path_matches_edge_list_path():
+    """large/main-batch.py:136-143 semantics: a batch given as MiniBatch (CSR-subset structure) == the same batch given as
+    (x[idx], subgraph(idx, edge_index, relabel_nodes=True))."""
+    from sgformer_b200 import kernels as K
+    from sgformer_b200 import large as L
+    from sgformer_b200.graph import Graph
+    from sgformer_b200.minibatch import RandomPartitionSampler
+    from sgformer_b200.synth import make_graph
+    n, d = 30000, 32
+    ei = make_graph(n, 200000, seed=5).to(DEV)
+    x = torch.randn(n, d, device=DEV)
+    y = torch.randint(0, 5, (n,), device=DEV)
+    model = L.SGFormer(d, 64, 5, gnn_num_layers=2, gnn_use_init=True, gnn_dropout=0.0, trans_dropout=0.0).to(DEV)
+    model.train()
+    sampler = RandomPartitionSampler(Graph(ei, n), x, y, batch_size=8000, generator=torch.Generator(device=DEV).manual_seed(0))
+    assert len(sampler) == 4
+    seen = 0
+    for mb in sampler:
+        out = model(mb)
+        ref = model(x[mb.idx], K.subgraph(ei, n, mb.idx))
+        _close(out, ref, 1e-5, 1e-6, "mini-batch logits")
+        torch.nn.functional.cross_entropy(out, mb.labels).backward()
+        seen += mb.idx.numel()
+    assert seen == n
+
+
 def test_host_resident_call_runs_on_gpu():
     """large/eval.py:35-65 `evaluate_large(device='cpu')` moves the model and data to the CPU and calls forward: the
     drop-in computes on the GPU and returns the logits on the host."""
