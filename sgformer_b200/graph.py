@@ -45,7 +45,7 @@ class Graph:
 
     @property
     def nnz(self) -> int:
-        return self.col.numel()
+        return int(self.rowptr[-1].item())
 
     @classmethod
     def _from_parts(cls, n, rowptr, col, dinv, transpose_same: bool):

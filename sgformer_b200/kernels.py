@@ -145,6 +145,7 @@ def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Te
     subset = subset.contiguous().to(torch.int64)
     b = subset.numel()
     dev = rowptr.device
+    trim = capacity is None
     if capacity is None:
         capacity = int((rowptr[subset + 1] - rowptr[subset]).sum().item()) if b else 0
     out_rowptr = torch.empty(b + 1, dtype=torch.int64, device=dev)
@@ -155,6 +156,8 @@ def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Te
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
     check(lib().sgf_csr_subset(_p(rowptr), _p(col), n, _p(subset), b, _p(node_map), _p(out_rowptr), _p(out_col), capacity,
                                _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_subset")
+    if trim:    # exact-size result (one more device sync); with a caller-provided capacity the tail of `col` is unused
+        out_col = out_col[:int(out_rowptr[b].item())]
     return out_rowptr, out_col, dinv[:b]
 
 

@@ -92,7 +92,7 @@ class SGFormer(SGFormerBase):
                            gnn_use_act=g.use_act, use_graph=bool(self.use_graph), graph_weight=float(self.graph_weight),
                            aggregate=self.aggregate)
 
-    def forward(self, x, edge_index):
+    def forward(self, x, edge_index=None):
         names, tensors = self._flat()
         if isinstance(x, MiniBatch):
             x, edge_index = x.features, x.graph
