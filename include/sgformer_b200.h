@@ -128,6 +128,10 @@ typedef struct {
     float nf;                                   /* ATTN_APPLY: node count N as float */
     float* den_out;                             /* ATTN_APPLY: [rows] fp32 or NULL */
     const float* r1_row; const float* r1_col;   /* AFFINE: optional rank-1 term + r1_row[r]*r1_col[c] (both or neither) */
+    float* col_sum; float* col_sumsq;           /* optional (caller-zeroed, fp32 [n_out]): column sums / sums of squares of the
+                                                   STORED output accumulated in the epilogue (BatchNorm statistics, K^T 1,
+                                                   ||Q||^2, ||K||^2 without a second pass); needs a 16-byte aligned out with a
+                                                   16-byte-multiple pitch and n_out <= 1024, else SGF_ERR_UNSUPPORTED */
 } sgf_gemm_nt_args;
 int sgf_gemm_nt(const sgf_gemm_nt_args* args /* host */, void* stream);
 

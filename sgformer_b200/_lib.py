@@ -33,6 +33,7 @@ class GemmNtArgs(C.Structure):
         ("nf", _f32),
         ("den_out", _vp),
         ("r1_row", _vp), ("r1_col", _vp),
+        ("col_sum", _vp), ("col_sumsq", _vp),
     ]
 
 

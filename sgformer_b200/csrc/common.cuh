@@ -45,25 +45,6 @@ __host__ inline int num_sms() {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t lane_id() {
-    uint32_t l;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
-    return l;
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-template <typename T> struct VecTraits;
-template <> struct VecTraits<float> { static constexpr int kPer16B = 4; };
-template <> struct VecTraits<__nv_bfloat16> { static constexpr int kPer16B = 8; };
-
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
@@ -273,14 +254,8 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a
 }
 
 // ------------------------------------------------------------------------------------------
-// counter-based dropout RNG (Philox-free: 64-bit mix of (seed, element index)); deterministic per element
+// counter-based dropout RNG (no mask tensor: the backward recomputes the mask)
 // ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t hash_u64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
-    x ^= x >> 33;
-    return static_cast<uint32_t>(x >> 11);
-}
 // Dropout of one 16-byte chunk (VN = 4 or 8 elements): one 64-bit hash per 4 elements, 16 random bits per element.
 // thr16 = round(p * 65536); an element is kept when its 16 bits >= thr16 and scaled by inv_keep = 65536 / (65536 - thr16).
 // The mask is a pure function of (seed, chunk_id) so the backward recomputes it (chunk_id = row * chunks_per_row + chunk).

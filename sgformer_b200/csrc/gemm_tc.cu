@@ -73,7 +73,9 @@ constexpr int B_BYTES_MAX = (256 + 16) * BK * 2;  // 34 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int STG_BYTES = BM * 128;               // output staging tile: 128 rows x 128 bytes (SW128), 2 per epilogue half
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + BAR_BYTES + 1024;
+constexpr int STAT_COLS = 1024;                   // fused column statistics cover n_out <= 1024
+constexpr int STAT_BYTES = 2 * STAT_COLS * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + BAR_BYTES + STAT_BYTES + 1024;
 
 struct Seg {
     int a_idx, a_koff, b_idx, b_koff, k_blocks;
@@ -95,6 +97,7 @@ struct Params {
     float nf; float* den_out;
     const float* r1_row; const float* r1_col;
     int tma_store;   // 1: epilogue stages 128-byte rows in smem and stores them with TMA; 0: direct global stores
+    float* col_sum; float* col_sumsq;   // optional fused column statistics of the STORED output (tma_store path only)
 };
 struct Tmaps {
     CUtensorMap a[SGF_MAX_SRC];
@@ -143,11 +146,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* stat_sm = reinterpret_cast<float*>(staging + 4 * STG_BYTES + BAR_BYTES);   // [2][STAT_COLS]: sum, sumsq
+    const bool want_stats = p.col_sum != nullptr || p.col_sumsq != nullptr;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int bn_total = p.bn_main + (p.has_tail ? 16 : 0);
     const int acc_stages = bn_total <= 256 ? 2 : 1;
+    if (want_stats)
+        for (int i = threadIdx.x; i < 2 * STAT_COLS; i += THREADS) stat_sm[i] = 0.f;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.n_seg; ++i) {
@@ -371,6 +378,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                         tma_store_2d(&tm.out, stg + buf * STG_BYTES, col_base + g * GW, m_blk * BM);
                         bulk_commit();
                     }
+                    if (want_stats) {
+                        // column sums of the staged (already rounded) tile: thread t of this half owns column t % GW and a
+                        // band of 128*GW/128 rows; the buffer is not rewritten before this half's next-but-one barrier
+                        const int th = (ew & 3) * 32 + lane;                  // 0..127 within the half
+                        const int cg = th % GW, band = th / GW, rows_band = BM / (128 / GW);
+                        const int colg = col_base + g * GW + cg;
+                        const int64_t valid_rows = p.rows - (int64_t)m_blk * BM;
+                        if (colg < p.n_out) {
+                            const uint8_t* tile = stg + buf * STG_BYTES;
+                            float s1 = 0.f, s2 = 0.f;
+                            for (int r = band * rows_band; r < (band + 1) * rows_band && r < valid_rows; ++r) {
+                                float v;
+                                if (p.out_dtype == 1) {
+                                    const int chunk = (cg >> 3) ^ (r & 7);
+                                    v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + r * 128 + chunk * 16 + (cg & 7) * 2));
+                                } else {
+                                    const int chunk = (cg >> 2) ^ (r & 7);
+                                    v = *reinterpret_cast<const float*>(tile + r * 128 + chunk * 16 + (cg & 3) * 4);
+                                }
+                                s1 += v;
+                                s2 += v * v;
+                            }
+                            atomicAdd(&stat_sm[colg], s1);
+                            atomicAdd(&stat_sm[STAT_COLS + colg], s2);
+                        }
+                    }
                     ++gcount;
                 }
             }
@@ -380,6 +413,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         if (p.tma_store && issuer) bulk_wait<0>();
+        if (want_stats) {
+            named_bar_sync(3, 32 * EPI_WARPS);
+            for (int i = threadIdx.x - 64; i < p.n_out; i += 32 * EPI_WARPS) {
+                if (p.col_sum) atomicAdd(&p.col_sum[i], stat_sm[i]);
+                if (p.col_sumsq) atomicAdd(&p.col_sumsq[i], stat_sm[STAT_COLS + i]);
+            }
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -597,6 +637,8 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
         const int es = a->out_dtype == 1 ? 2 : 4;
         p.tma_store = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ldo * es) % 16 == 0) ? 1 : 0;
         if (p.tma_store && (rc = make_tmap_2d(&tm.out, a->out, a->out_dtype, a->rows, a->n_out, a->ldo, nt::BM))) return rc;
+        p.col_sum = a->col_sum; p.col_sumsq = a->col_sumsq;
+        if ((p.col_sum || p.col_sumsq) && (!p.tma_store || a->n_out > nt::STAT_COLS)) return SGF_ERR_UNSUPPORTED;
     }
 
     static bool attr_set = false;

@@ -98,7 +98,7 @@ def input_operand(x: Tensor, prec: Precision) -> K.Operand:
 # linear attention core (full_attention_conv)
 # =================================================================================================
 def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precision, tape: Optional[Tape],
-                      comm: Comm = SINGLE) -> Tensor:
+                      comm: Comm = SINGLE, stats=None) -> Tensor:
     """q,k: [N, H*M], v: [N, H*D] activations (views allowed) -> o [N, H*D].  medium/ours.py:14-34.
     One Frobenius norm over all heads (medium/ours.py:16-17); N is the query count (the GLOBAL node count when the rows
     are sharded: the un-normalised partials {S', z', ||q||^2, ||k||^2} are all-reduced once, C1)."""
@@ -107,8 +107,11 @@ def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precisi
     m = q.shape[1] // heads
     d = v.shape[1] // heads
     dev = q.device
-    _, sq_q = K.colstats(q, want_sum=False)
-    z_raw, sq_k = K.colstats(k)
+    if stats is not None:        # (sum of squares of q columns, column sums of k, sum of squares of k columns) from the
+        sq_q, z_raw, sq_k = stats    # producing GEMM's epilogue
+    else:
+        _, sq_q = K.colstats(q, want_sum=False)
+        z_raw, sq_k = K.colstats(k)
     s_list = []
     for hd in range(heads):
         kh, vh = k[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
@@ -208,12 +211,14 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
         wcat, bcat = _qkv_weight(P, lp, use_weight)
         nout = wcat.shape[0]
         qkv = torch.empty((n, K.ceil_to(nout, 8)), dtype=prec.act_dtype, device=dev)[:, :nout]
+        csum = torch.zeros(nout, dtype=torch.float32, device=dev)
+        csq = torch.zeros(nout, dtype=torch.float32, device=dev)
         K.gemm_nt([K.as_operand(x, prec.planes)], [K.pack_operand(wcat, False, prec.planes)], [(0, 0, 0, 0, h)], nout, qkv,
-                  bias=bcat)
+                  bias=bcat, col_sum=csum, col_sumsq=csq)        # K^T 1, ||Q||^2, ||K||^2 fall out of the projection's epilogue
         q, k = qkv[:, :H * h], qkv[:, H * h:2 * H * h]
         v = qkv[:, 2 * H * h:] if use_weight else x
         at = Tape() if tape is not None else None
-        o = attention_forward(q, k, v, H, prec, at, comm)
+        o = attention_forward(q, k, v, H, prec, at, comm, stats=(csq[:H * h], csum[H * h:2 * H * h], csq[H * h:2 * H * h]))
         a = K.head_mean(o, H, h) if H > 1 else o
         y, st = K.ln_fwd(a, x if use_res else None, ca, cb, P.get(f"{pfx}bns.{i + 1}.weight"), P.get(f"{pfx}bns.{i + 1}.bias"),
                          use_ln, bool(cfg["trans_use_act"]), p, seed + 211 + i, tape is not None)
@@ -304,12 +309,20 @@ def _tile_heads(da: Tensor, heads: int) -> Tensor:
 # =================================================================================================
 # GraphConv branch (large / 100M)
 # =================================================================================================
-def _bn_stats(z: Tensor, P, name: str, use_bn: bool, training: bool, zbias: Optional[Tensor] = None, comm: Comm = SINGLE):
+def _stat_bufs(use_bn: bool, training: bool, h: int, dev):
+    """Zeroed (sum, sumsq) buffers for a GEMM epilogue to fill when batch statistics are needed, else (None, None)."""
+    if use_bn and training:
+        return torch.zeros(h, dtype=torch.float32, device=dev), torch.zeros(h, dtype=torch.float32, device=dev)
+    return None, None
+
+
+def _bn_stats(z: Tensor, P, name: str, use_bn: bool, training: bool, zbias: Optional[Tensor] = None, comm: Comm = SINGLE,
+              pre=None):
     if not use_bn:
         return None, None
     h = z.shape[1]
     if training:
-        s, q = K.colstats(z)
+        s, q = pre if (pre is not None and pre[0] is not None) else K.colstats(z)
         comm.allreduce_(s, q)                                              # C3: batch statistics span all shards
         rows = comm.n_global if comm.active else z.shape[0]
         mean, rstd = K.bn_finalize(s, q, rows, h, zbias, P.get(name + "running_mean"), P.get(name + "running_var"),
@@ -335,9 +348,10 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     use_bn, use_res, use_act = bool(cfg["gnn_use_bn"]), bool(cfg["gnn_use_residual"]), bool(cfg["gnn_use_act"])
     use_init, use_weight = bool(cfg["gnn_use_init"]), bool(cfg["gnn_use_weight"])
     dinv = graph.dinv
+    st0 = _stat_bufs(use_bn, training, h, dev)
     z0 = K.gemm_nt([xin], [_w(P, pfx + "fcs.0.weight", prec)], [(0, 0, 0, 0, d_in)], h,
-                   K.alloc_act(n, h, prec.act_dtype, dev), bias=P[pfx + "fcs.0.bias"])
-    mean0, rstd0 = _bn_stats(z0, P, pfx + "bns.0.", use_bn, training, comm=comm)
+                   K.alloc_act(n, h, prec.act_dtype, dev), bias=P[pfx + "fcs.0.bias"], col_sum=st0[0], col_sumsq=st0[1])
+    mean0, rstd0 = _bn_stats(z0, P, pfx + "bns.0.", use_bn, training, comm=comm, pre=st0)
     last_is_input = nl == 0
     x0, cur_s = K.bn_fwd(z0, None, mix if last_is_input else None, mean0, rstd0, P.get(pfx + "bns.0.weight"),
                          P.get(pfx + "bns.0.bias"), None, use_bn, True, p, seed + 307, gw, dinv, True, not last_is_input)
@@ -348,18 +362,20 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     for i in range(nl):
         last = i == nl - 1
         y = K.spmm(graph.rowptr, graph.col, dinv, comm.allgather_rows(cur_s))    # C4: operand rows of every shard
+        st = _stat_bufs(use_bn, training, h, dev)      # BatchNorm sums come out of the GEMM epilogue
         if use_init:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
             z = K.gemm_nt([K.as_operand(y, prec.planes), K.as_operand(x0, prec.planes)], [w],
-                          [(0, 0, 0, 0, h), (1, 0, 0, h, h)], h, K.new_like(y), bias=P[f"{pfx}convs.{i}.W.bias"])
+                          [(0, 0, 0, 0, h), (1, 0, 0, h, h)], h, K.new_like(y), bias=P[f"{pfx}convs.{i}.W.bias"],
+                          col_sum=st[0], col_sumsq=st[1])
         elif use_weight:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
             z = K.gemm_nt([K.as_operand(y, prec.planes)], [w], [(0, 0, 0, 0, h)], h, K.new_like(y),
-                          bias=P[f"{pfx}convs.{i}.W.bias"])
+                          bias=P[f"{pfx}convs.{i}.W.bias"], col_sum=st[0], col_sumsq=st[1])
         else:
-            z = y
+            z, st = y, (None, None)
         name = f"{pfx}bns.{i + 1}."
-        mean, rstd = _bn_stats(z, P, name, use_bn, training, comm=comm)
+        mean, rstd = _bn_stats(z, P, name, use_bn, training, comm=comm, pre=st)
         yo, ys = K.bn_fwd(z, x0 if use_res else None, mix if last else None, mean, rstd, P.get(name + "weight"),
                           P.get(name + "bias"), None, use_bn, use_act, p, seed + 401 + i, gw, dinv, last, not last)
         if tape is not None:

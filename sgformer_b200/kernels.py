@@ -249,7 +249,8 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
             row_scale: Optional[Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
             alpha_dev: Optional[Tensor] = None, beta_dev: Optional[Tensor] = None, relu: bool = False,
             accumulate: bool = False, tail: Optional[Operand] = None, nf: float = 0.0, den_out: Optional[Tensor] = None,
-            r1_row: Optional[Tensor] = None, r1_col: Optional[Tensor] = None) -> Tensor:
+            r1_row: Optional[Tensor] = None, r1_col: Optional[Tensor] = None, col_sum: Optional[Tensor] = None,
+            col_sumsq: Optional[Tensor] = None) -> Tensor:
     """out[rows, n_out] = epilogue(sum over `pairs` (ai, a_k0, bi, b_k0, klen) of A[ai][:, a_k0:+klen] . B[bi][:, b_k0:+klen]^T).
 
     Logical K offsets; 3-plane operands expand every pair into the six bf16x3 partial products."""
@@ -302,8 +303,22 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
     args.relu, args.accumulate = int(relu), int(accumulate)
     args.nf, args.den_out = nf, _p(_f32vec(den_out, rows, "den_out"))
     args.r1_row, args.r1_col = _p(_f32vec(r1_row, rows, "r1_row")), _p(_f32vec(r1_col, n_out, "r1_col"))
+    fused_stats = (col_sum is not None or col_sumsq is not None) and stats_fusable(out)
+    if fused_stats:
+        args.col_sum, args.col_sumsq = _p(_f32vec(col_sum, n_out, "col_sum")), _p(_f32vec(col_sumsq, n_out, "col_sumsq"))
     check(lib().sgf_gemm_nt(C.byref(args), _stream()), "sgf_gemm_nt")
+    if (col_sum is not None or col_sumsq is not None) and not fused_stats:
+        s_, q_ = colstats(out, want_sum=col_sum is not None, want_sumsq=col_sumsq is not None)   # unaligned output: extra pass
+        if col_sum is not None:
+            col_sum.add_(s_)
+        if col_sumsq is not None:
+            col_sumsq.add_(q_)
     return out
+
+
+def stats_fusable(out: Tensor) -> bool:
+    """Whether sgf_gemm_nt can accumulate column statistics of `out` in its epilogue (TMA-store path, n_out <= 1024)."""
+    return out.data_ptr() % 16 == 0 and (out.stride(0) * out.element_size()) % 16 == 0 and out.shape[1] <= 1024
 
 
 def _tn_once(a: Tensor, lda: int, m: int, b: Tensor, ldb: int, n: int, rows: int, out: Tensor, transpose_out: bool,

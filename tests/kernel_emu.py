@@ -96,7 +96,7 @@ def as_operand(x, planes):
 
 def gemm_nt(A, B, pairs, n_out, out, *, epi=EPI_AFFINE, bias=None, aux=None, row_scale=None, alpha=1.0, beta=0.0,
             alpha_dev=None, beta_dev=None, relu=False, accumulate=False, tail=None, nf=0.0, den_out=None, r1_row=None,
-            r1_col=None):
+            r1_col=None, col_sum=None, col_sumsq=None):
     acc = 0
     for (ai, ak, bi, bk, klen) in pairs:
         acc = acc + A[ai].data[:, ak:ak + klen] @ B[bi].data[:, bk:bk + klen].t()
@@ -122,7 +122,12 @@ def gemm_nt(A, B, pairs, n_out, out, *, epi=EPI_AFFINE, bias=None, aux=None, row
             v = v * row_scale[:, None]
     if accumulate:
         v = v + out.float()
-    return _st(out, v)
+    _st(out, v)
+    if col_sum is not None:
+        col_sum += out.float().sum(0)
+    if col_sumsq is not None:
+        col_sumsq += (out.float() ** 2).sum(0)
+    return out
 
 
 def gemm_tn(A, B, out, *, transpose_out=False, alpha=1.0, beta=0.0, alpha_dev=None):

@@ -345,6 +345,25 @@ def test_gemm_nt_affine(K, rows, k, n_out, planes):
     _close(out, oe, tol, tol, "full epilogue")
 
 
+@pytest.mark.parametrize("rows,k,n_out,dtype", [(1000, 64, 64, torch.bfloat16), (130, 256, 256, torch.bfloat16),
+                                                 (4097, 256, 768, torch.bfloat16), (777, 128, 96, torch.float32),
+                                                 (3000, 256, 256, torch.float32), (5, 32, 16, torch.bfloat16)])
+def test_gemm_nt_fused_column_stats(K, rows, k, n_out, dtype):
+    """Column sums / sums of squares of the STORED output from the GEMM epilogue == a colstats pass over the output."""
+    g = torch.Generator().manual_seed(rows)
+    a, b = torch.randn(rows, k, generator=g), torch.randn(n_out, k, generator=g) / k ** 0.5
+    bias = torch.randn(n_out, generator=g)
+    planes = 1 if dtype == torch.bfloat16 else 3
+    A, B = K.pack_operand(a.to(DEV), False, planes), K.pack_operand(b.to(DEV), False, planes)
+    out = K.alloc_act(rows, n_out, dtype, DEV)
+    cs, cq = torch.zeros(n_out, device=DEV), torch.zeros(n_out, device=DEV)
+    K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, out, bias=bias.to(DEV), col_sum=cs, col_sumsq=cq)
+    s_ref, q_ref = K.colstats(out)
+    _close(cs, s_ref, 1e-5, 1e-3, "fused column sums")
+    _close(cq, q_ref, 1e-5, 1e-3, "fused column sums of squares")
+    _close(cs, out.float().sum(0), 1e-4, 1e-2, "vs torch sum")
+
+
 @pytest.mark.parametrize("planes", [1, 3])
 @pytest.mark.parametrize("h", [16, 32, 64, 256])
 def test_gemm_nt_concat_segments(K, planes, h):
