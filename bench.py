@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--ref-nodes", type=int, default=60000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rmat", action="store_true", help="power-law R-MAT edges instead of uniform (secondary, not graded)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--parallel", default="dp", choices=["dp", "rows"],
                     help="N>1: 'dp' = rank-local graph partitions + gradient all-reduce (weak scaling); 'rows' = ONE graph, "
@@ -208,7 +209,9 @@ def main():
     from sgformer_b200 import large as L
     from sgformer_b200.graph import get_graph
     from sgformer_b200.loss import nll_loss_from_logits
-    from sgformer_b200.synth import make_graph
+    from sgformer_b200.synth import make_graph, make_rmat_graph
+    if args.rmat:
+        make_graph = make_rmat_graph
 
     torch.manual_seed(1234)
     n, d, c, h = w["n"], w["d"], w["c"], w["h"]
@@ -430,6 +433,7 @@ def main():
                         f"dp{world}: rank-local graph partitions, replicated model, NCCL grad allreduce"),
                        "step": "zero_grad + forward + fused log_softmax/NLL (sgf_softmax_nll) + backward + fused Adam",
                        "cuda_graph": used_graph,
+                       "edges": "rmat(.57,.19,.19)" if args.rmat else "uniform",
                        "l2": "inputs (>= 1 GB of activations per pass) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -26,3 +26,23 @@ def make_graph(n: int, e_stored: int, seed: int = 0, device="cpu") -> torch.Tens
     row, col = row[keep], col[keep]
     loops = torch.arange(n, device=device)
     return torch.stack([torch.cat([row, loops]), torch.cat([col, loops])]).contiguous()
+
+
+def make_rmat_graph(n: int, e_stored: int, seed: int = 0, device="cpu", a: float = 0.57, b: float = 0.19, c: float = 0.19) -> torch.Tensor:
+    """Power-law (R-MAT, a=.57 b=c=.19) variant of `make_graph` (SURVEY.md §8d secondary workload): skewed degrees with hub
+    rows, same symmetrise / self-loop post-processing.  Node ids are drawn in [0, 2^ceil(log2 n)) and folded into [0, n)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    bits = max(1, (n - 1).bit_length())
+    src = torch.zeros(e_stored, dtype=torch.int64, device=device)
+    dst = torch.zeros(e_stored, dtype=torch.int64, device=device)
+    for _ in range(bits):
+        r = torch.rand(e_stored, generator=g, device=device)
+        src = src * 2 + (r >= a + b).long()                       # quadrants c, d set the source bit
+        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()   # quadrants b, d set the target bit
+    src, dst = src % n, dst % n
+    key = torch.unique(torch.cat([src * n + dst, dst * n + src]))
+    row, col = key // n, key % n
+    keep = row != col
+    row, col = row[keep], col[keep]
+    loops = torch.arange(n, device=device)
+    return torch.stack([torch.cat([row, loops]), torch.cat([col, loops])]).contiguous()
