@@ -90,7 +90,16 @@ int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t n, const i
  * Pure HBM-bound gather: 128-bit loads of neighbour rows, fp32 accumulation, no tensor cores.
  * ------------------------------------------------------------------------------------------------ */
 int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
-             void* y, int64_t ldy, int64_t n_rows, int h, int dtype, void* stream);
+             void* y, int64_t ldy, int64_t n_rows, int h, int dtype,
+             int64_t max_row_len /* 0: all rows; > 0: rows longer than this are skipped and must be produced by sgf_spmm_heavy */,
+             void* stream);
+/* Hub rows of power-law graphs: the rows `heavy_rows[i]` (those longer than max_row_len) are cut into segments
+ * [seg_start[s], seg_start[s] + seg_len[s]) of the col array (segments of row i: heavy_seg_ptr[i] .. heavy_seg_ptr[i+1]);
+ * one warp gathers one segment into partial[s, :h] (fp32 workspace [n_seg, h]) and a second kernel adds a row's partials in
+ * order (deterministic), applies row_scale and writes y[heavy_rows[i], :]. */
+int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y, int64_t ldy, int h,
+                   int dtype, const int64_t* seg_start, const int32_t* seg_len, int64_t n_seg, float* partial,
+                   const int64_t* heavy_rows, const int64_t* heavy_seg_ptr, int64_t n_heavy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 tensor cores (bf16 operands staged by TMA, fp32 accumulation in TMEM).

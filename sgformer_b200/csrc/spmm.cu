@@ -23,10 +23,52 @@ namespace sgf {
 constexpr int kSpmmBlock = 256;
 constexpr int kUnroll = 4;
 
+// gather-accumulate the neighbour rows col[s..e) of x into acc (fp32), all lane groups of the warp cooperating
+template <typename T, int CPL>
+__device__ __forceinline__ void gather_range(const int32_t* __restrict__ col, const T* __restrict__ x, int64_t ldx, int64_t s, int64_t e,
+                                             int lane, int groups, int grp, const int (&coff)[CPL], const bool (&cval)[CPL],
+                                             float (&acc)[CPL][Vec16<T>::N]) {
+    constexpr int VN = Vec16<T>::N;
+    for (int64_t base = s; base < e; base += 32) {
+        const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+        const int my_idx = lane < cnt ? ldg_nc_na_s32(col + base + lane) : -1;
+        for (int j0 = 0; j0 < cnt; j0 += groups * kUnroll) {
+            uint4 v[kUnroll][CPL];
+            int nb[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                int j = j0 + u * groups + grp;
+                int t = __shfl_sync(0xffffffffu, my_idx, j & 31);
+                nb[u] = j < cnt ? t : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
+                    else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    float f[VN];
+                    Vec16<T>::unpack(v[u][c], f);
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) acc[c][i] += f[i];
+                }
+        }
+    }
+}
+
+// one warp per output row; rows longer than max_len (> 0) are left to the segmented path below
 template <typename T, int CPL>
 __global__ void __launch_bounds__(kSpmmBlock, 4)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
-                 const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2) {
+                 const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2,
+                 int64_t max_len) {
     constexpr int VN = Vec16<T>::N;
     const int lane = threadIdx.x & 31;
     const int lpr = 1 << lpr_log2;
@@ -35,8 +77,6 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     const int sub = lane & (lpr - 1);
     const int64_t warp0 = ((int64_t)blockIdx.x * kSpmmBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kSpmmBlock) >> 5;
-
-    // per-lane chunk offsets (elements) and validity
     int coff[CPL];
     bool cval[CPL];
 #pragma unroll
@@ -45,49 +85,16 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
         cval[c] = ch < chunks;
         coff[c] = ch * VN;
     }
-
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
         const int64_t s = rowptr[r];
         const int64_t e = rowptr[r + 1];
+        if (max_len > 0 && e - s > max_len) continue;
         float acc[CPL][VN];
 #pragma unroll
         for (int c = 0; c < CPL; ++c)
 #pragma unroll
             for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
-
-        for (int64_t base = s; base < e; base += 32) {
-            const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
-            const int my_idx = lane < cnt ? ldg_nc_na_s32(col + base + lane) : -1;
-            for (int j0 = 0; j0 < cnt; j0 += groups * kUnroll) {
-                uint4 v[kUnroll][CPL];
-                int nb[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    int j = j0 + u * groups + grp;
-                    int t = __shfl_sync(0xffffffffu, my_idx, j & 31);
-                    nb[u] = j < cnt ? t : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) {
-                        if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
-                        else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) {
-                        float f[VN];
-                        Vec16<T>::unpack(v[u][c], f);
-#pragma unroll
-                        for (int i = 0; i < VN; ++i) acc[c][i] += f[i];
-                    }
-            }
-        }
-        // fold the neighbour groups
+        gather_range<T, CPL>(col, x, ldx, s, e, lane, groups, grp, coff, cval, acc);
         for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
@@ -109,9 +116,72 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
     }
 }
 
+// hub rows (power-law graphs): a row longer than the threshold is cut into segments, one warp per segment writes an fp32
+// partial sum, and a second kernel adds a row's partials in fixed order (deterministic), scales and stores the row.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kSpmmBlock, 4)
+spmm_segments_kernel(const int32_t* __restrict__ col, const T* __restrict__ x, int64_t ldx, const int64_t* __restrict__ seg_start,
+                     const int32_t* __restrict__ seg_len, int64_t n_seg, float* __restrict__ partial, int h, int chunks,
+                     int lpr_log2) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int lpr = 1 << lpr_log2;
+    const int groups = 32 >> lpr_log2;
+    const int grp = lane >> lpr_log2;
+    const int sub = lane & (lpr - 1);
+    const int64_t warp0 = ((int64_t)blockIdx.x * kSpmmBlock + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kSpmmBlock) >> 5;
+    int coff[CPL];
+    bool cval[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int ch = sub + c * lpr;
+        cval[c] = ch < chunks;
+        coff[c] = ch * VN;
+    }
+    for (int64_t sg = warp0; sg < n_seg; sg += nwarps) {
+        const int64_t s = seg_start[sg];
+        float acc[CPL][VN];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
+        gather_range<T, CPL>(col, x, ldx, s, s + seg_len[sg], lane, groups, grp, coff, cval, acc);
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], o);
+        }
+        if (grp == 0) {
+            float* dst = partial + sg * h;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+                if (cval[c])
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) dst[coff[c] + i] = acc[c][i];
+        }
+    }
+}
+
+template <typename T>
+__global__ void spmm_heavy_finalize_kernel(const float* __restrict__ partial, const int64_t* __restrict__ heavy_rows,
+                                           const int64_t* __restrict__ heavy_seg_ptr, int64_t n_heavy,
+                                           const float* __restrict__ row_scale, T* __restrict__ y, int64_t ldy, int h) {
+    const int64_t total = n_heavy * h;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / h;
+        const int c = (int)(t - i * h);
+        float s = 0.f;
+        for (int64_t sg = heavy_seg_ptr[i]; sg < heavy_seg_ptr[i + 1]; ++sg) s += partial[sg * h + c];
+        const int64_t r = heavy_rows[i];
+        y[r * ldy + c] = from_f32<T>(s * (row_scale ? row_scale[r] : 1.f));
+    }
+}
+
 template <typename T>
 static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
-                       void* y, int64_t ldy, int64_t n_rows, int h, cudaStream_t st) {
+                       void* y, int64_t ldy, int64_t n_rows, int h, int64_t max_len, cudaStream_t st) {
     constexpr int VN = Vec16<T>::N;
     if (h % VN != 0 || ldx % VN != 0 || ldy % VN != 0) return SGF_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return SGF_ERR_ARG;
@@ -130,7 +200,7 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* r
 #define SGF_SPMM_CASE(N)                                                                                              \
     case N:                                                                                                           \
         spmm_rows_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy,      \
-                                                                        n_rows, chunks, lpr_log2);                     \
+                                                                        n_rows, chunks, lpr_log2, max_len);            \
         break;
     switch (cpl) {
         SGF_SPMM_CASE(1)
@@ -145,13 +215,68 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* r
     return SGF_OK;
 }
 
+template <typename T>
+static int launch_heavy(const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y, int64_t ldy, int h,
+                        const int64_t* seg_start, const int32_t* seg_len, int64_t n_seg, float* partial,
+                        const int64_t* heavy_rows, const int64_t* heavy_seg_ptr, int64_t n_heavy, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    if (h % VN != 0 || ldx % VN != 0) return SGF_ERR_ARG;
+    const int chunks = h / VN;
+    int lpr_log2 = 0;
+    while ((1 << lpr_log2) < chunks && lpr_log2 < 5) ++lpr_log2;
+    const int lpr = 1 << lpr_log2;
+    const int cpl = (chunks + lpr - 1) / lpr;
+    int64_t blocks = (n_seg * 32 + kSpmmBlock - 1) / kSpmmBlock;
+    int64_t cap = (int64_t)num_sms() * 4 * 8;
+    if (blocks > cap) blocks = cap;
+    const T* xp = static_cast<const T*>(x);
+#define SGF_SEG_CASE(N)                                                                                                 \
+    case N:                                                                                                             \
+        spmm_segments_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(col, xp, ldx, seg_start, seg_len, n_seg, partial, \
+                                                                            h, chunks, lpr_log2);                       \
+        break;
+    switch (cpl) {
+        SGF_SEG_CASE(1)
+        SGF_SEG_CASE(2)
+        SGF_SEG_CASE(3)
+        SGF_SEG_CASE(4)
+        default: return SGF_ERR_UNSUPPORTED;
+    }
+#undef SGF_SEG_CASE
+    SGF_LAUNCH_CHECK();
+    count_launch();
+    int64_t fb = (n_heavy * h + 255) / 256;
+    if (fb > cap) fb = cap;
+    spmm_heavy_finalize_kernel<T><<<(unsigned)fb, 256, 0, st>>>(partial, heavy_rows, heavy_seg_ptr, n_heavy, row_scale,
+                                                                static_cast<T*>(y), ldy, h);
+    SGF_LAUNCH_CHECK();
+    count_launch();
+    return SGF_OK;
+}
+
 }  // namespace sgf
 
 extern "C" int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
-                        void* y, int64_t ldy, int64_t n_rows, int h, int dtype, void* stream) {
-    if (!rowptr || n_rows < 0 || h <= 0 || (n_rows > 0 && (!x || !y))) return SGF_ERR_ARG;
+                        void* y, int64_t ldy, int64_t n_rows, int h, int dtype, int64_t max_row_len, void* stream) {
+    if (!rowptr || n_rows < 0 || h <= 0 || (n_rows > 0 && (!x || !y)) || max_row_len < 0) return SGF_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == 0) return sgf::launch_spmm<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, st);
-    if (dtype == 1) return sgf::launch_spmm<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, st);
+    if (dtype == 0) return sgf::launch_spmm<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st);
+    if (dtype == 1) return sgf::launch_spmm<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st);
+    return SGF_ERR_ARG;
+}
+
+extern "C" int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y, int64_t ldy, int h,
+                              int dtype, const int64_t* seg_start, const int32_t* seg_len, int64_t n_seg, float* partial,
+                              const int64_t* heavy_rows, const int64_t* heavy_seg_ptr, int64_t n_heavy, void* stream) {
+    if (!col || !x || !y || h <= 0 || n_seg < 0 || n_heavy < 0) return SGF_ERR_ARG;
+    if (n_seg == 0 || n_heavy == 0) return SGF_OK;
+    if (!seg_start || !seg_len || !partial || !heavy_rows || !heavy_seg_ptr) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0)
+        return sgf::launch_heavy<float>(col, row_scale, x, ldx, y, ldy, h, seg_start, seg_len, n_seg, partial, heavy_rows,
+                                        heavy_seg_ptr, n_heavy, st);
+    if (dtype == 1)
+        return sgf::launch_heavy<__nv_bfloat16>(col, row_scale, x, ldx, y, ldy, h, seg_start, seg_len, n_seg, partial, heavy_rows,
+                                                heavy_seg_ptr, n_heavy, st);
     return SGF_ERR_ARG;
 }

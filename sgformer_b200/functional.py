@@ -254,7 +254,7 @@ class SpMMFn(Function):
     @staticmethod
     def forward(ctx, x, graph: Graph, prec):
         xs = K.axpby(_to_act(x, prec), None, 1.0, 0.0, row_scale=graph.dinv)
-        y = K.spmm(graph.rowptr, graph.col, graph.dinv, xs)
+        y = K.spmm(graph.rowptr, graph.col, graph.dinv, xs, heavy=graph.heavy)
         ctx.state = (graph, prec, x.dtype)
         return _from_act(y, x.dtype)
 
@@ -263,7 +263,7 @@ class SpMMFn(Function):
         graph, prec, dtx = ctx.state
         rp, cl = graph.transpose()
         ds = K.axpby(_to_act(dy, prec), None, 1.0, 0.0, row_scale=graph.dinv)
-        dx = K.spmm(rp, cl, graph.dinv, ds)
+        dx = K.spmm(rp, cl, graph.dinv, ds, heavy=graph.heavy_t)
         ctx.state = None
         return _from_act(dx, dtx), None, None
 

@@ -41,6 +41,8 @@ class Graph:
         self.self_loop_mode = self_loop_mode
         self.edge_index = edge_index
         self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True, rows=rows)
+        self.heavy = K.heavy_rows(self.rowptr)      # segment plan for hub rows (None on graphs without them)
+        self.heavy_t = None
         self._t: Optional[Tuple[Tensor, Tensor]] = None
 
     @property
@@ -52,6 +54,7 @@ class Graph:
         g = cls.__new__(cls)
         g.n, g.rows, g.self_loop_mode, g.edge_index = int(n), None, 0, None
         g.rowptr, g.col, g.dinv = rowptr, col, dinv
+        g.heavy = g.heavy_t = None       # batch subgraphs: no per-batch sync for a hub plan
         g._t = (rowptr, col) if transpose_same else None
         return g
 
@@ -75,9 +78,11 @@ class Graph:
         if self._t is None:
             if _is_symmetric(self.edge_index, self.n):
                 self._t = (self.rowptr, self.col)      # also true per row shard: rows r0..r1 of A^T == rows of A
+                self.heavy_t = self.heavy
             else:
                 rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)
                 self._t = (rp, cl)
+                self.heavy_t = K.heavy_rows(rp)
         return self._t
 
 

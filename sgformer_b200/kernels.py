@@ -6,6 +6,7 @@ Nothing here touches CPU tensors: a non-CUDA tensor raises — there is no fallb
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -161,7 +162,36 @@ def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Te
     return out_rowptr, out_col, dinv[:b]
 
 
-def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+HEAVY_ROW = 1024      # rows longer than this are processed in segments of HEAVY_ROW entries (hub rows of power-law graphs)
+
+
+@dataclass
+class HeavyRows:
+    """Segment plan for the rows longer than HEAVY_ROW (built once per CSR by `heavy_rows`)."""
+    rows: Tensor       # int64 [nh]
+    seg_ptr: Tensor    # int64 [nh+1]
+    seg_start: Tensor  # int64 [ns]
+    seg_len: Tensor    # int32 [ns]
+
+
+def heavy_rows(rowptr: Tensor) -> Optional[HeavyRows]:
+    """Plan for the hub rows of a CSR, or None when no row exceeds HEAVY_ROW (one device sync; graph-build time)."""
+    lens = rowptr[1:] - rowptr[:-1]
+    rows = (lens > HEAVY_ROW).nonzero().flatten()
+    if rows.numel() == 0:
+        return None
+    nseg = (lens[rows] + HEAVY_ROW - 1) // HEAVY_ROW
+    seg_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rowptr.device)
+    seg_ptr[1:] = torch.cumsum(nseg, 0)
+    owner = torch.repeat_interleave(torch.arange(rows.numel(), device=rowptr.device), nseg)
+    k = torch.arange(owner.numel(), device=rowptr.device) - seg_ptr[owner]
+    seg_start = rowptr[rows][owner] + k * HEAVY_ROW
+    seg_len = torch.minimum(rowptr[rows + 1][owner] - seg_start, torch.full_like(seg_start, HEAVY_ROW)).to(torch.int32)
+    return HeavyRows(rows.contiguous(), seg_ptr, seg_start.contiguous(), seg_len.contiguous())
+
+
+def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, out: Optional[Tensor] = None,
+         heavy: Optional[HeavyRows] = None) -> Tensor:
     _use(x)
     n = rowptr.numel() - 1
     rows, h, ldx = _mat(x, "x")
@@ -174,8 +204,15 @@ def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, ou
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib().sgf_spmm(_p(rowptr), _p(col), _p(_f32vec(row_scale, n, "row_scale")), _p(x), ldx, _p(out), ldy, n, h,
-                         dcode(x), _stream()), "sgf_spmm")
+    rs = _f32vec(row_scale, n, "row_scale")
+    check(lib().sgf_spmm(_p(rowptr), _p(col), _p(rs), _p(x), ldx, _p(out), ldy, n, h, dcode(x),
+                         HEAVY_ROW if heavy is not None else 0, _stream()), "sgf_spmm")
+    if heavy is not None:
+        ns = heavy.seg_start.numel()
+        partial = torch.empty((ns, h), dtype=torch.float32, device=x.device)
+        check(lib().sgf_spmm_heavy(_p(col), _p(rs), _p(x), ldx, _p(out), ldy, h, dcode(x), _p(heavy.seg_start),
+                                   _p(heavy.seg_len), ns, _p(partial), _p(heavy.rows), _p(heavy.seg_ptr), heavy.rows.numel(),
+                                   _stream()), "sgf_spmm_heavy")
     if ev is not None:
         e1.record()
         ev.append((e0, e1))
@@ -316,9 +353,15 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
     return out
 
 
+# Measured on B200 (products shape): accumulating the statistics in the GEMM epilogue costs more epilogue issue slots than the
+# separate 0.31 ms colstats pass it saves (105.3 vs 101.4 ms/step), so the fused path is opt-in.
+FUSE_GEMM_STATS = os.environ.get("SGF_FUSED_STATS", "0") == "1"
+
+
 def stats_fusable(out: Tensor) -> bool:
-    """Whether sgf_gemm_nt can accumulate column statistics of `out` in its epilogue (TMA-store path, n_out <= 1024)."""
-    return out.data_ptr() % 16 == 0 and (out.stride(0) * out.element_size()) % 16 == 0 and out.shape[1] <= 1024
+    """Whether sgf_gemm_nt accumulates the column statistics of `out` in its epilogue (TMA-store path, n_out <= 1024)."""
+    return FUSE_GEMM_STATS and out.data_ptr() % 16 == 0 and (out.stride(0) * out.element_size()) % 16 == 0 and \
+        out.shape[1] <= 1024
 
 
 def _tn_once(a: Tensor, lda: int, m: int, b: Tensor, ldb: int, n: int, rows: int, out: Tensor, transpose_out: bool,

@@ -66,7 +66,7 @@ def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True, 
     return rowptr, val[order].to(torch.int32), dinv
 
 
-def spmm(rowptr, col, row_scale, x, out=None):
+def spmm(rowptr, col, row_scale, x, out=None, heavy=None):
     n = rowptr.numel() - 1
     rows = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
     y = torch.zeros((n, x.shape[1]), dtype=torch.float32).index_add_(0, rows, x.float()[col.long()])
@@ -335,6 +335,7 @@ class EmuGraph:
     def __init__(self, edge_index, n, self_loop_mode=0, rows=None):
         self.n, self.edge_index, self.self_loop_mode, self.rows = n, edge_index, self_loop_mode, rows
         self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True, rows=rows)
+        self.heavy = self.heavy_t = None
 
     def transpose(self):
         rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)

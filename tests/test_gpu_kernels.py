@@ -171,6 +171,29 @@ def test_spmm_matches_scipy(K, dtype, h):
         _close(lhs, rhs, 1e-5, 1e-5, "spmm linearity")
 
 
+@pytest.mark.parametrize("dtype,h", [(torch.float32, 64), (torch.bfloat16, 256), (torch.bfloat16, 64)])
+def test_spmm_hub_rows_segmented_path(K, dtype, h):
+    """Power-law graphs: rows longer than kernels.HEAVY_ROW go through the segmented (deterministic) path."""
+    from sgformer_b200.synth import make_rmat_graph
+    n = 30000
+    ei = make_rmat_graph(n, 600000, seed=1)
+    rowptr, col, dinv = K.csr_build(ei.to(DEV), n)
+    plan = K.heavy_rows(rowptr)
+    lens = (rowptr[1:] - rowptr[:-1])
+    assert plan is not None and plan.rows.numel() == int((lens > K.HEAVY_ROW).sum()) and int(lens.max()) > 4 * K.HEAVY_ROW
+    assert int(plan.seg_len.sum()) == int(lens[plan.rows].sum())
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(3)).to(DEV).to(dtype)
+    xs = K.axpby(x, None, 1.0, 0.0, row_scale=dinv)
+    y = K.spmm(rowptr, col, dinv, xs, heavy=plan)
+    ref = np_ref.spmm_fp64(ei.numpy(), n, x.float().cpu().numpy())
+    tol = 1e-5 if dtype == torch.float32 else 1.5e-2
+    _close(y.float(), ref, tol, tol * 1e-2, "spmm with hub rows")
+    y2 = K.spmm(rowptr, col, dinv, xs, heavy=plan)
+    assert torch.equal(y, y2), "segmented path must be deterministic"
+    y_plain = K.spmm(rowptr, col, dinv, xs)      # single-warp path on the same rows
+    _close(y.float(), y_plain.float(), tol, tol * 1e-2, "segmented vs plain")
+
+
 # ------------------------------------------------------------------------------------------------
 # row kernels vs the kernel contract
 # ------------------------------------------------------------------------------------------------
@@ -348,7 +371,7 @@ def test_gemm_nt_affine(K, rows, k, n_out, planes):
 @pytest.mark.parametrize("rows,k,n_out,dtype", [(1000, 64, 64, torch.bfloat16), (130, 256, 256, torch.bfloat16),
                                                  (4097, 256, 768, torch.bfloat16), (777, 128, 96, torch.float32),
                                                  (3000, 256, 256, torch.float32), (5, 32, 16, torch.bfloat16)])
-def test_gemm_nt_fused_column_stats(K, rows, k, n_out, dtype):
+def test_gemm_nt_fused_column_stats(K, monkeypatch, rows, k, n_out, dtype):
     """Column sums / sums of squares of the STORED output from the GEMM epilogue == a colstats pass over the output."""
     g = torch.Generator().manual_seed(rows)
     a, b = torch.randn(rows, k, generator=g), torch.randn(n_out, k, generator=g) / k ** 0.5
@@ -357,6 +380,7 @@ def test_gemm_nt_fused_column_stats(K, rows, k, n_out, dtype):
     A, B = K.pack_operand(a.to(DEV), False, planes), K.pack_operand(b.to(DEV), False, planes)
     out = K.alloc_act(rows, n_out, dtype, DEV)
     cs, cq = torch.zeros(n_out, device=DEV), torch.zeros(n_out, device=DEV)
+    monkeypatch.setattr(K, "FUSE_GEMM_STATS", True)     # the fused path is opt-in (see kernels.FUSE_GEMM_STATS)
     K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, out, bias=bias.to(DEV), col_sum=cs, col_sumsq=cq)
     s_ref, q_ref = K.colstats(out)
     _close(cs, s_ref, 1e-5, 1e-3, "fused column sums")

@@ -160,35 +160,29 @@ def test_graphconv_layer_golden():
             _close(layer.W.weight.grad, c["dW"], 1e-3, 1e-4, f"{name} dW")
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
-@pytest.mark.parametrize("n,e,d,h,c,kw", [
-    (20000, 150000, 128, 256, 40, dict(gnn_num_layers=3, graph_weight=0.5)),                       # arxiv recipe, large/run.sh:2-5
-    (30000, 400000, 100, 256, 47, dict(gnn_num_layers=3, gnn_use_init=True, graph_weight=0.5)),    # amazon2m recipe, :15-19
-    (25000, 300000, 65, 64, 2, dict(gnn_num_layers=2, gnn_use_init=True, graph_weight=0.5)),       # pokec recipe, :22-26
-])
-def test_model_matches_oracle_midsize(n, e, d, h, c, kw, precision, tol):
-    """Fresh seeded graph, reference hyper-parameters, sizes the CPU oracle finishes in seconds."""
+MIDSIZE = [
+    (12000, 90000, 128, 256, 40, dict(gnn_num_layers=3, graph_weight=0.5)),                       # arxiv recipe, large/run.sh:2-5
+    (16000, 200000, 100, 256, 47, dict(gnn_num_layers=3, gnn_use_init=True, graph_weight=0.5)),    # amazon2m recipe, :15-19
+    (14000, 160000, 65, 64, 2, dict(gnn_num_layers=2, gnn_use_init=True, graph_weight=0.5)),       # pokec recipe, :22-26
+]
+_midsize_cache = {}
+
+
+def _midsize_oracle(i):
+    """Oracle results of case i (computed once, shared by both precisions; the CPU oracle is the slow part)."""
+    if i in _midsize_cache:
+        return _midsize_cache[i]
     from sgformer_b200.synth import make_graph
-    from sgformer_b200 import large as L
+    n, e, d, h, c, kw = MIDSIZE[i]
     cfg = O.make_config("large", d, h, c, gnn_dropout=0.0, trans_dropout=0.0, trans_use_act=False, **kw)
     sd = O.init_state_dict(cfg, seed=3)
     ei = make_graph(n, e, seed=1)
     g = torch.Generator().manual_seed(2)
     x = torch.randn(n, d, generator=g)
-    ref = O.sgformer_forward(cfg, sd, x, ei, training=False)
-    model = L.SGFormer(d, h, c, trans_dropout=0.0, gnn_dropout=0.0, trans_use_act=False, **kw).to(DEV).set_precision(precision)
-    model.load_state_dict(sd)
-    model.eval()
-    with torch.no_grad():
-        out = model(x.to(DEV), ei.to(DEV))
-    _close(out, ref, tol, tol, "eval logits")
-    # train-mode forward (batch statistics) + loss + gradients.  The weight gradients behind a BatchNorm are ill-conditioned
-    # (the fp32 torch reference itself is only good to ~2e-3 of their scale here), so gradients are judged against an fp64 run
-    # of the oracle: in fp32 mode the CUDA path must be within max(1e-2 of the tensor's scale, 8x the fp32 oracle's own
-    # deviation, 1e-4 of the largest gradient entry of the model); in bf16 mode gradients are bounded in Frobenius norm.
     y = torch.randint(0, c, (n,), generator=g)
+    ref_eval = O.sgformer_forward(cfg, sd, x, ei, training=False)
 
-    def oracle_grads(dtype):
+    def grads(dtype):
         sdg = {k: (v.to(dtype).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
                    (v.to(dtype) if v.is_floating_point() else v.clone())) for k, v in sd.items()}
         out = O.sgformer_forward(cfg, sdg, x.to(dtype), ei, training=True)
@@ -196,14 +190,36 @@ def test_model_matches_oracle_midsize(n, e, d, h, c, kw, precision, tol):
         loss.backward()
         return out.detach(), loss.detach(), {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
 
-    ref_t, loss_ref, g32 = oracle_grads(torch.float32)
-    _, _, g64 = oracle_grads(torch.float64)
+    ref_t, loss_ref, g32 = grads(torch.float32)
+    _, _, g64 = grads(torch.float64)
+    _midsize_cache[i] = dict(cfg=cfg, sd=sd, ei=ei, x=x, y=y, ref_eval=ref_eval, ref_t=ref_t, loss_ref=loss_ref, g32=g32, g64=g64)
+    return _midsize_cache[i]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("case", range(len(MIDSIZE)))
+def test_model_matches_oracle_midsize(case, precision, tol):
+    """Fresh seeded graph, reference hyper-parameters, sizes the CPU oracle finishes in seconds.
+    Train-mode gradients: the weight gradients behind a BatchNorm are ill-conditioned (the fp32 torch reference itself is only
+    good to ~2e-3 of their scale here), so they are judged against an fp64 run of the oracle: in fp32 mode the CUDA path must be
+    within max(1e-2 of the tensor's scale, 8x the fp32 oracle's own deviation, 1e-4 of the largest gradient entry of the model);
+    in bf16 mode gradients are bounded in Frobenius norm."""
+    from sgformer_b200 import large as L
+    n, e, d, h, c, kw = MIDSIZE[case]
+    r = _midsize_oracle(case)
+    x, ei, y, g32, g64 = r["x"], r["ei"], r["y"], r["g32"], r["g64"]
+    model = L.SGFormer(d, h, c, trans_dropout=0.0, gnn_dropout=0.0, trans_use_act=False, **kw).to(DEV).set_precision(precision)
+    model.load_state_dict(r["sd"])
+    model.eval()
+    with torch.no_grad():
+        out = model(x.to(DEV), ei.to(DEV))
+    _close(out, r["ref_eval"], tol, tol, "eval logits")
     model.train()
     out_t = model(x.to(DEV), ei.to(DEV))
     loss = torch.nn.functional.cross_entropy(out_t, y.to(DEV))
     loss.backward()
-    _close(out_t, ref_t, tol, tol, "train logits")
-    _close(loss, loss_ref, tol, tol, "loss")
+    _close(out_t, r["ref_t"], tol, tol, "train logits")
+    _close(loss, r["loss_ref"], tol, tol, "loss")
     problems = []
     gmax = max(v.norm().item() for v in g64.values())
     gabs = max(v.abs().max().item() for v in g64.values())
