@@ -150,12 +150,30 @@ __global__ void __launch_bounds__(kRowBlock, 3) colstats_kernel(const T* __restr
     Lane<T, CPL> L(chunks, lpr_log2);
     float s1[CPL][VN], s2[CPL][VN];
     SGF_ZERO(s1) SGF_ZERO(s2)
+    // four rows in flight per lane group (packed) before the accumulation: a pure reduction has no other latency hiding
+    constexpr int U = 4;
 #pragma unroll 1
-    for (int64_t r = L.row0; r < rows; r += L.row_step) {
-        float f[CPL][VN];
-        L.load(x, ldx, r, f);
-        const float wr = w ? w[r] : 1.f;
-        SGF_FOR_ELEMS { s1[c][i] += wr * f[c][i]; s2[c][i] += f[c][i] * f[c][i]; }
+    for (int64_t r = L.row0; r < rows; r += U * L.row_step) {
+        uint4 raw[U][CPL];
+        float wr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t ru = r + u * L.row_step;
+            if (ru < rows) {
+                L.load_raw(x, ldx, ru, raw[u]);
+                wr[u] = w ? w[ru] : 1.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) raw[u][c] = make_uint4(0u, 0u, 0u, 0u);
+                wr[u] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float f[CPL][VN];
+            L.unpack(raw[u], f);
+            SGF_FOR_ELEMS { s1[c][i] += wr[u] * f[c][i]; s2[c][i] += f[c][i] * f[c][i]; }
+        }
     }
     if (sum) flush_columns<T, CPL>(L, s1, sm, h, sum);
     if (sumsq) flush_columns<T, CPL>(L, s2, sm, h, sumsq);
