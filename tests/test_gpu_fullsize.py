@@ -1,0 +1,100 @@
+"""Size-independent properties at BASELINE.json's full shapes (where the CPU oracle would take minutes): the CSR invariants,
+A.1 = degree (exact), linearity and the adjoint identity of the SpMM, conservation laws of the linear attention, and the
+induced-subgraph / CSR-subset consistency, on the ogbn-products- and Pokec-shaped synthetic graphs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def products():
+    from sgformer_b200.graph import Graph
+    from sgformer_b200.synth import SHAPES, make_graph
+    n, d, e, c, h, layers, use_init = SHAPES["products"]
+    ei = make_graph(n, e, seed=0, device=DEV)
+    return n, ei, Graph(ei, n)
+
+
+def test_csr_invariants_products_shape(products):
+    n, ei, g = products
+    rowptr, col = g.rowptr, g.col
+    assert rowptr[0].item() == 0 and rowptr[-1].item() == ei.shape[1] == col.numel()      # nnz conserved
+    lens = rowptr[1:] - rowptr[:-1]
+    assert bool((lens >= 1).all())                                                         # every node has its self loop
+    assert torch.equal(lens, torch.bincount(ei[1], minlength=n))                           # in-degree over `col` (bit-exact)
+    # sortedness inside rows: a position may decrease only where a new row starts
+    dec = (col[1:] < col[:-1]).nonzero().flatten() + 1
+    starts = torch.zeros(col.numel() + 1, dtype=torch.bool, device=DEV)
+    starts[rowptr] = True
+    assert bool(starts[dec].all())
+    assert int(col.min()) >= 0 and int(col.max()) < n
+    assert torch.equal(g.dinv, (1.0 / lens.float()).sqrt())                                # same op order as the reference
+    rp_t, col_t = g.transpose()
+    assert rp_t is g.rowptr                                                                # symmetric edge set detected
+    # checksum of checksums: sum of column ids per row, summed over rows == sum over the edge list
+    assert int(col.sum(dtype=torch.int64)) == int(ei[0].sum())
+
+
+def test_spmm_properties_products_shape(products):
+    from sgformer_b200 import kernels as K
+    n, ei, g = products
+    ones = torch.ones(n, 8, device=DEV)
+    deg = K.spmm(g.rowptr, g.col, None, ones, heavy=g.heavy)
+    assert torch.equal(deg[:, 0], (g.rowptr[1:] - g.rowptr[:-1]).float())                 # A.1 = degree, exact in fp32
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(n, 64, generator=gen, device=DEV)
+    y = torch.randn(n, 64, generator=gen, device=DEV)
+    ax, ay = K.spmm(g.rowptr, g.col, None, x), K.spmm(g.rowptr, g.col, None, y)
+    lin = K.spmm(g.rowptr, g.col, None, K.axpby(x, y, 1.0, 2.0))
+    err = (lin - (ax + 2 * ay)).abs().max().item() / ax.abs().max().item()
+    assert err < 1e-5, f"linearity: {err:.2e}"
+    # adjoint identity on the symmetric graph: <A x, y> == <x, A y>
+    lhs, rhs = (ax.double() * y.double()).sum().item(), (x.double() * ay.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-3, f"adjoint: {lhs} vs {rhs}"
+    # bf16 path at h=256 (the benchmarked configuration) against the fp32 path on the same (bf16-rounded) input
+    xb = torch.randn(n, 256, generator=gen, device=DEV).to(torch.bfloat16)
+    yb = K.spmm(g.rowptr, g.col, g.dinv, xb)
+    yf = K.spmm(g.rowptr, g.col, g.dinv, xb.float())
+    rel = (yb.float() - yf).abs().max().item() / yf.abs().max().item()
+    assert rel < 8e-3, f"bf16 vs fp32 SpMM: {rel:.2e}"
+
+
+def test_attention_conservation_laws_pokec_shape():
+    """With v = 1 every output is exactly 1 (num = q~.z + N = den); with q = 0 the output is v (pure residual term)."""
+    from sgformer_b200 import engine as E
+    n, h = 1632803, 64
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    q = torch.randn(n, h, generator=gen, device=DEV)
+    k = torch.randn(n, h, generator=gen, device=DEV)
+    v1 = torch.ones(n, h, device=DEV)
+    o = E.attention_forward(q, k, v1, 1, E.FP32, None)
+    assert (o - 1).abs().max().item() < 1e-5
+    v = torch.randn(n, h, generator=gen, device=DEV)
+    o0 = E.attention_forward(torch.full_like(q, 1e-30), k, v, 1, E.FP32, None)   # q ~ 0 (the Frobenius norm must not be 0)
+    tape = E.Tape()
+    o = E.attention_forward(q, k, v, 1, E.FP32, tape)
+    # the attention term is O(N^-1.5) of the residual term (SURVEY.md TL;DR 3): outputs stay within 1e-4 of v ...
+    assert (o - v).abs().max().item() < 1e-3
+    # ... while the pass-1 partial is checked against a chunked fp64 reduction
+    s_ref = torch.zeros(h, h, dtype=torch.float64, device=DEV)
+    for i in range(0, n, 1 << 18):
+        s_ref += k[i:i + (1 << 18)].double().t() @ v[i:i + (1 << 18)].double()
+    rel = (tape["s"][0].double() - s_ref).abs().max().item() / s_ref.abs().max().item()
+    assert rel < 1e-4, f"S' = k^T v at N = 1.6 M: {rel:.2e}"
+    assert torch.isfinite(o0).all()
+
+
+def test_subgraph_consistency_products_shape(products):
+    from sgformer_b200 import kernels as K
+    n, ei, g = products
+    idx = torch.randperm(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))[:100000]
+    sub = g.subset(idx)
+    ei_sub = K.subgraph(ei, n, idx)
+    rp, cl, dv = K.csr_build(ei_sub, idx.numel())
+    assert torch.equal(sub.rowptr, rp) and torch.equal(sub.col, cl) and torch.equal(sub.dinv, dv)
+    # idempotence: the subset of everything in natural order is the graph itself
+    small = g.subset(torch.arange(0, 50000, device=DEV))
+    again = small.__class__._from_parts(small.n, small.rowptr, small.col, small.dinv, True)
+    assert torch.equal(small.rowptr, again.rowptr)
