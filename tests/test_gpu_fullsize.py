@@ -62,7 +62,7 @@ def test_spmm_properties_products_shape(products):
 
 
 def test_attention_conservation_laws_pokec_shape():
-    """With v = 1 every output is exactly 1 (num = q~.z + N = den); with q = 0 the output is v (pure residual term)."""
+    """With v = 1 every output is exactly 1 (num = q~.z + N = den); in general the output stays within O(N^-1.5) of v."""
     from sgformer_b200 import engine as E
     n, h = 1632803, 64
     gen = torch.Generator(device=DEV).manual_seed(1)
@@ -72,7 +72,6 @@ def test_attention_conservation_laws_pokec_shape():
     o = E.attention_forward(q, k, v1, 1, E.FP32, None)
     assert (o - 1).abs().max().item() < 1e-5
     v = torch.randn(n, h, generator=gen, device=DEV)
-    o0 = E.attention_forward(torch.full_like(q, 1e-30), k, v, 1, E.FP32, None)   # q ~ 0 (the Frobenius norm must not be 0)
     tape = E.Tape()
     o = E.attention_forward(q, k, v, 1, E.FP32, tape)
     # the attention term is O(N^-1.5) of the residual term (SURVEY.md TL;DR 3): outputs stay within 1e-4 of v ...
@@ -83,7 +82,7 @@ def test_attention_conservation_laws_pokec_shape():
         s_ref += k[i:i + (1 << 18)].double().t() @ v[i:i + (1 << 18)].double()
     rel = (tape["s"][0].double() - s_ref).abs().max().item() / s_ref.abs().max().item()
     assert rel < 1e-4, f"S' = k^T v at N = 1.6 M: {rel:.2e}"
-    assert torch.isfinite(o0).all()
+    assert torch.isfinite(o).all()
 
 
 def test_subgraph_consistency_products_shape(products):
@@ -94,7 +93,6 @@ def test_subgraph_consistency_products_shape(products):
     ei_sub = K.subgraph(ei, n, idx)
     rp, cl, dv = K.csr_build(ei_sub, idx.numel())
     assert torch.equal(sub.rowptr, rp) and torch.equal(sub.col, cl) and torch.equal(sub.dinv, dv)
-    # idempotence: the subset of everything in natural order is the graph itself
-    small = g.subset(torch.arange(0, 50000, device=DEV))
-    again = small.__class__._from_parts(small.n, small.rowptr, small.col, small.dinv, True)
-    assert torch.equal(small.rowptr, again.rowptr)
+    # idempotence: the subset of all nodes in natural order is the graph itself
+    full = g.subset(torch.arange(n, device=DEV))
+    assert torch.equal(full.rowptr, g.rowptr) and torch.equal(full.col, g.col) and torch.equal(full.dinv, g.dinv)
