@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kRowBlock, 3) ln_fwd_kernel(const T* __restric
 }
 
 template <typename T, int CPL, bool DROP>
-__global__ void __launch_bounds__(kRowBlock, 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ rr,
+__global__ void __launch_bounds__(kRowBlock, 3) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ rr,
                                                             int64_t ld, int64_t rows, int h, int chunks, int lpr_log2, float a, float b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ stats, int use_ln, int use_relu, float p,
