@@ -1,5 +1,5 @@
 """torchrun script (not a pytest file): row-sharded execution on N GPUs over NCCL must reproduce the single-GPU result.
-Run by scripts/gpu_multi.sh:  torchrun --nproc-per-node N tests/multi_gpu_check.py"""
+Run by scripts/gpu_multi_bench.sh:  torchrun --nproc-per-node N tests/multi_gpu_check.py"""
 import os
 import sys
 
