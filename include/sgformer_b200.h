@@ -118,6 +118,9 @@ int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, in
 #define SGF_EPI_AFFINE 0      /* out = (alpha*acc + beta*aux[r,c] + bias[c] + r1_row[r]*r1_col[c]) -> relu -> *row_scale[r] (+= out) */
 #define SGF_EPI_ATTN_APPLY 1  /* out[r,c] = (acc[r,c] + nf*aux[r,c]) / (acc_tail[r,0] + nf); den_out[r] = that denominator */
 
+#define SGF_GEMM_AUTO 0
+#define SGF_GEMM_STREAM_B 1
+#define SGF_GEMM_RESIDENT_B 2
 typedef struct {
     const void* a[SGF_MAX_SRC]; int64_t lda[SGF_MAX_SRC]; int64_t a_cols[SGF_MAX_SRC];
     const void* b[SGF_MAX_SRC]; int64_t ldb[SGF_MAX_SRC]; int64_t b_cols[SGF_MAX_SRC];
@@ -141,6 +144,10 @@ typedef struct {
                                                    STORED output accumulated in the epilogue (BatchNorm statistics, K^T 1,
                                                    ||Q||^2, ||K||^2 without a second pass); needs a 16-byte aligned out with a
                                                    16-byte-multiple pitch and n_out <= 1024, else SGF_ERR_UNSUPPORTED */
+    int32_t schedule;                           /* SGF_GEMM_AUTO (0), or force one of the two schedules (tests / tuning):
+                                                   SGF_GEMM_STREAM_B = weights stream through the TMA ring with A,
+                                                   SGF_GEMM_RESIDENT_B = weights of one n-block stay in shared memory across the
+                                                   row tiles (SGF_ERR_UNSUPPORTED if they do not fit) */
 } sgf_gemm_nt_args;
 int sgf_gemm_nt(const sgf_gemm_nt_args* args /* host */, void* stream);
 

@@ -34,6 +34,7 @@ class GemmNtArgs(C.Structure):
         ("den_out", _vp),
         ("r1_row", _vp), ("r1_col", _vp),
         ("col_sum", _vp), ("col_sumsq", _vp),
+        ("schedule", _i32),
     ]
 
 

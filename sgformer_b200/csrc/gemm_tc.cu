@@ -72,10 +72,19 @@ constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES_MAX = (256 + 16) * BK * 2;  // 34 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int STG_BYTES = BM * 128;               // output staging tile: 128 rows x 128 bytes (SW128), 2 per epilogue half
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 512;
 constexpr int STAT_COLS = 1024;                   // fused column statistics cover n_out <= 1024
 constexpr int STAT_BYTES = 2 * STAT_COLS * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + BAR_BYTES + STAT_BYTES + 1024;
+// Resident-B mode (p.b_res): the whole B operand of one n-block (all k-blocks) stays in shared memory across the row tiles
+// of a CTA, so that only A streams through the ring.  Without it every 128-row tile re-fetches K x n_block of weights from
+// L2 and the kernel runs into the L2->SM throughput cap (~12 TB/s) before the HBM roofline (ncu, profiles/r1b_*).
+constexpr int RES_BYTES = (256 + 16) * 256 * 2;   // 136 KB: K = 256 x (256 + 16-column tail)
+constexpr int RES_MAX_KB = 16;                    // one full/empty mbarrier pair per resident k-block
+constexpr int RES_STAGES = 3;                     // A-only ring
+constexpr int RES_STG = 2;                        // one staging tile per epilogue half
+constexpr int SMEM_BYTES_RES = RES_BYTES + RES_STAGES * A_BYTES + RES_STG * STG_BYTES + BAR_BYTES + STAT_BYTES + 1024;
+static_assert(SMEM_BYTES <= 232448 && SMEM_BYTES_RES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 struct Seg {
     int a_idx, a_koff, b_idx, b_koff, k_blocks;
@@ -84,6 +93,8 @@ struct Params {
     int64_t rows;
     int n_out, bn_main, has_tail, n_blocks;
     int64_t num_tiles;
+    int b_res;          // 1: resident-B schedule (see RES_BYTES)
+    int64_t chunk;      // b_res: row tiles per CTA between two reloads of B (only matters when n_blocks > 1)
     int n_seg, total_kb;
     Seg seg[SGF_MAX_SEG];
     int epi;
@@ -106,29 +117,6 @@ struct Tmaps {
     CUtensorMap out;
 };
 
-__device__ __forceinline__ void load16(const void* base, int dtype, int64_t off, float* f) {
-    if (dtype == 1) {
-        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off);
-        uint4 u0 = __ldg(p), u1 = __ldg(p + 1);
-        Vec16<__nv_bfloat16>::unpack(u0, f);
-        Vec16<__nv_bfloat16>::unpack(u1, f + 8);
-    } else {
-        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) Vec16<float>::unpack(__ldg(p + i), f + 4 * i);
-    }
-}
-__device__ __forceinline__ void store16(void* base, int dtype, int64_t off, const float* f) {
-    if (dtype == 1) {
-        uint4* p = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off);
-        p[0] = Vec16<__nv_bfloat16>::pack(f);
-        p[1] = Vec16<__nv_bfloat16>::pack(f + 8);
-    } else {
-        uint4* p = reinterpret_cast<uint4*>(static_cast<float*>(base) + off);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = Vec16<float>::pack(f + 4 * i);
-    }
-}
 __device__ __forceinline__ float load1(const void* base, int dtype, int64_t off) {
     return dtype == 1 ? __bfloat162float(static_cast<const __nv_bfloat16*>(base)[off]) : static_cast<const float*>(base)[off];
 }
@@ -136,17 +124,111 @@ __device__ __forceinline__ void store1(void* base, int dtype, int64_t off, float
     if (dtype == 1) static_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
     else static_cast<float*>(base)[off] = v;
 }
+// 8 consecutive elements starting at element offset `off` (vec: 16-byte aligned and all 8 valid; else the first nv, rest 0)
+__device__ __forceinline__ void load8(const void* base, int dtype, int64_t off, bool vec, int nv, float* f) {
+    if (vec) {
+        if (dtype == 1) {
+            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off), f);
+        } else {
+            const uint4* q = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
+            Vec16<float>::unpack(q[0], f);
+            Vec16<float>::unpack(q[1], f + 4);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = j < nv ? load1(base, dtype, off + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void store8(void* base, int dtype, int64_t off, bool vec, int nv, const float* f) {
+    if (vec) {
+        if (dtype == 1) {
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off) = Vec16<__nv_bfloat16>::pack(f);
+        } else {
+            uint4* q = reinterpret_cast<uint4*>(static_cast<float*>(base) + off);
+            q[0] = Vec16<float>::pack(f);
+            q[1] = Vec16<float>::pack(f + 4);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nv) store1(base, dtype, off + j, f[j]);
+    }
+}
+
+// The three warp roles walk the CTA's tiles in the same order.
+//  streaming:  tile = blockIdx.x + i*gridDim.x over (m_blk, n_blk) pairs, n_blk fastest.
+//  resident-B: the CTA owns row tiles m = blockIdx.x + i*gridDim.x; they are visited in chunks of p.chunk, and inside a chunk
+//              n_blk is the OUTER loop: B(n_blk) is loaded once per (chunk, n_blk) "group", the chunk's A tiles are re-read
+//              from L2 for the following n-blocks (a chunk is sized to stay L2-resident).
+struct TileIter {
+    const Params& p;
+    bool started = false;
+    int64_t tile = 0;                 // streaming
+    int64_t cnt = 0, c0 = 0, i = 0;   // resident
+    int nb = 0;
+    int64_t group = 0;
+    int m_blk = 0, n_blk = 0;
+    bool first = false, last = false;   // first / last tile of its group (resident)
+    __device__ explicit TileIter(const Params& pp) : p(pp) {
+        if (p.b_res) {
+            const int64_t m_tiles = p.num_tiles / p.n_blocks;
+            cnt = m_tiles > blockIdx.x ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        }
+    }
+    __device__ bool next() {
+        if (!p.b_res) {
+            tile = started ? tile + gridDim.x : blockIdx.x;
+            started = true;
+            if (tile >= p.num_tiles) return false;
+            m_blk = (int)(tile / p.n_blocks);
+            n_blk = (int)(tile % p.n_blocks);
+            return true;
+        }
+        if (!started) {
+            started = true;
+            if (cnt == 0) return false;
+        } else {
+            ++i;
+            const int64_t cend = c0 + p.chunk < cnt ? c0 + p.chunk : cnt;
+            if (i >= cend) {
+                ++group;
+                if (++nb >= p.n_blocks) {
+                    nb = 0;
+                    c0 += p.chunk;
+                    if (c0 >= cnt) return false;
+                }
+                i = c0;
+            }
+        }
+        const int64_t cend = c0 + p.chunk < cnt ? c0 + p.chunk : cnt;
+        m_blk = (int)(blockIdx.x + i * gridDim.x);
+        n_blk = nb;
+        first = i == c0;
+        last = i == cend - 1;
+        return true;
+    }
+};
 
 __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ Tmaps tm, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* staging = smem + STAGES * STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(staging + 4 * STG_BYTES);
+    // streaming: [ring: STAGES x (A | B)] [staging 4 tiles];  resident: [B: RES_BYTES] [ring: RES_STAGES x A] [staging 2 tiles]
+    const bool res = p.b_res != 0;
+    uint8_t* bres = smem;
+    uint8_t* ring = res ? smem + RES_BYTES : smem;
+    const int ring_stages = res ? RES_STAGES : STAGES;
+    const int ring_stride = res ? A_BYTES : STAGE_BYTES;
+    const int stg_per_half = res ? RES_STG / 2 : 2;
+    uint8_t* staging = ring + ring_stages * ring_stride;
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * stg_per_half * STG_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* stat_sm = reinterpret_cast<float*>(staging + 4 * STG_BYTES + BAR_BYTES);   // [2][STAT_COLS]: sum, sumsq
+    uint64_t* bres_full = tmem_empty + 2;
+    uint64_t* bres_empty = bres_full + RES_MAX_KB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_empty + RES_MAX_KB);
+    float* stat_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + BAR_BYTES);   // [2][STAT_COLS]: sum, sumsq
+    static_assert((2 * STAGES + 4 + 2 * RES_MAX_KB) * 8 + 4 <= BAR_BYTES, "barrier area");
+    static_assert(RES_STAGES <= STAGES, "ring barriers");
     const bool want_stats = p.col_sum != nullptr || p.col_sumsq != nullptr;
 
     const int warp = threadIdx.x >> 5;
@@ -165,6 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
         if (p.tma_store) tma_prefetch_desc(&tm.out);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        for (int s = 0; s < RES_MAX_KB; ++s) { mbar_init(&bres_full[s], 1); mbar_init(&bres_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -179,21 +262,36 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            const uint32_t stage_tx = A_BYTES + p.bn_main * BK * 2 + (p.has_tail ? 16 * BK * 2 : 0);
+            const uint32_t b_tx = p.bn_main * BK * 2 + (p.has_tail ? 16 * BK * 2 : 0);
             int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_blk = (int)(tile / p.n_blocks), n_blk = (int)(tile % p.n_blocks);
+            TileIter ti(p);
+            while (ti.next()) {
+                int kbg = 0;
                 for (int s = 0; s < p.n_seg; ++s) {
                     const Seg sg = p.seg[s];
-                    for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                    for (int kb = 0; kb < sg.k_blocks; ++kb, ++kbg) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = smem + stage * STAGE_BYTES;
-                        uint8_t* sb = sa + A_BYTES;
-                        mbar_arrive_expect_tx(&full[stage], stage_tx);
-                        tma_load_2d(sa, &tm.a[sg.a_idx], &full[stage], sg.a_koff + kb * BK, m_blk * BM);
-                        tma_load_2d(sb, &tm.b[sg.b_idx], &full[stage], sg.b_koff + kb * BK, n_blk * p.bn_main);
-                        if (p.has_tail) tma_load_2d(sb + p.bn_main * BK * 2, &tm.tail, &full[stage], sg.b_koff + kb * BK, 0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        uint8_t* sa = ring + stage * ring_stride;
+                        if (!res) {
+                            uint8_t* sb = sa + A_BYTES;
+                            mbar_arrive_expect_tx(&full[stage], A_BYTES + b_tx);
+                            tma_load_2d(sa, &tm.a[sg.a_idx], &full[stage], sg.a_koff + kb * BK, ti.m_blk * BM);
+                            tma_load_2d(sb, &tm.b[sg.b_idx], &full[stage], sg.b_koff + kb * BK, ti.n_blk * p.bn_main);
+                            if (p.has_tail) tma_load_2d(sb + p.bn_main * BK * 2, &tm.tail, &full[stage], sg.b_koff + kb * BK, 0);
+                        } else {
+                            // A first (its ring slot frees early), then - on the first tile of a group - the k-block of B,
+                            // as soon as the previous group's last tile has consumed the old one
+                            mbar_arrive_expect_tx(&full[stage], A_BYTES);
+                            tma_load_2d(sa, &tm.a[sg.a_idx], &full[stage], sg.a_koff + kb * BK, ti.m_blk * BM);
+                            if (ti.first) {
+                                mbar_wait(&bres_empty[kbg], (uint32_t)(ti.group & 1) ^ 1);
+                                uint8_t* sb = bres + (size_t)kbg * b_tx;
+                                mbar_arrive_expect_tx(&bres_full[kbg], b_tx);
+                                tma_load_2d(sb, &tm.b[sg.b_idx], &bres_full[kbg], sg.b_koff + kb * BK, ti.n_blk * p.bn_main);
+                                if (p.has_tail) tma_load_2d(sb + p.bn_main * BK * 2, &tm.tail, &bres_full[kbg], sg.b_koff + kb * BK, 0);
+                            }
+                        }
+                        if (++stage == ring_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -203,19 +301,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             // ===== MMA issuer =====
             const uint32_t idesc_main = make_idesc_bf16(BM, p.bn_main, 0, 0);
             const uint32_t idesc_tail = make_idesc_bf16(BM, 16, 0, 0);
+            const uint32_t b_tx = p.bn_main * BK * 2 + (p.has_tail ? 16 * BK * 2 : 0);
             int stage = 0; uint32_t phase = 0;
             int64_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            TileIter ti(p);
+            for (; ti.next(); ++it) {
                 const int acc = (int)(it % acc_stages);
                 const uint32_t acc_phase = (uint32_t)((it / acc_stages) & 1);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_main = tmem_base + acc * 256;
                 for (int kbg = 0; kbg < p.total_kb; ++kbg) {
+                    if (res && ti.first) mbar_wait(&bres_full[kbg], (uint32_t)(ti.group & 1));
                     mbar_wait(&full[stage], phase);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
+                    const uint32_t sa = smem_u32(ring + stage * ring_stride);
+                    const uint32_t sb = res ? smem_u32(bres) + (uint32_t)kbg * b_tx : sa + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
@@ -228,8 +329,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                         }
                     }
                     umma_commit(&empty[stage]);
+                    if (res && ti.last) umma_commit(&bres_empty[kbg]);
                     if (kbg == p.total_kb - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == ring_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -247,21 +349,42 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
         const bool vecf_ok = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                              (!p.r1_col || (reinterpret_cast<uintptr_t>(p.r1_col) & 15) == 0);
         const int GW = p.out_dtype == 1 ? 64 : 32;            // columns per 128-byte staging row
-        uint8_t* stg = staging + half * 2 * STG_BYTES;
+        uint8_t* stg = staging + half * stg_per_half * STG_BYTES;
         const bool issuer = ((ew & 3) == 0) && lane == 0;    // one TMA-store issuing thread per half
         const int r_local = q * 32 + lane;
+        // The addend of the epilogue (aux, else the old output when accumulating) is fetched one 32-column piece AHEAD as
+        // packed 16-byte chunks: a thread owns a whole row, so an un-prefetched load costs a full DRAM latency per piece
+        // (r1b: GEMMs with aux/accumulate ran 2x slower than those without).  16-bit sources only (4 registers / 32 columns... x4).
+        const void* pre_src = p.aux ? p.aux : (p.accumulate ? p.out : nullptr);
+        const int64_t pre_ld = p.aux ? p.ld_aux : p.ldo;
+        const bool pre_on = pre_src && (p.aux ? p.aux_dtype == 1 && aux_vec_ok : p.out_dtype == 1 && vec_ok);
+        uint4 pre[4];
+        bool pre_ok = false;     // pre[] holds the addend of the NEXT piece to be processed
+        auto prefetch = [&](int64_t row, bool row_ok, int col0) {
+            pre_ok = pre_on && row_ok && col0 + 32 <= p.n_out;
+            if (pre_ok) {
+                const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(pre_src) + row * pre_ld + col0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pre[c] = p.aux ? ldg_nc_na(src + c) : src[c];
+            }
+        };
+        const int n_pieces = (p.bn_main + 31) / 32;
+        const int ppg = GW / 32;                                   // pieces per staging group (bf16: 2, fp32: 1)
+        const int n_groups = (n_pieces + ppg - 1) / ppg;
         uint32_t gcount = 0;
         int64_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = (int)(tile / p.n_blocks), n_blk = (int)(tile % p.n_blocks);
+        TileIter ti(p);
+        for (; ti.next(); ++it) {
+            const int m_blk = ti.m_blk, n_blk = ti.n_blk;
             const int acc = (int)(it % acc_stages);
             const uint32_t acc_phase = (uint32_t)((it / acc_stages) & 1);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tcgen05_fence_after();
             const int64_t row = (int64_t)m_blk * BM + r_local;
             const bool row_ok = row < p.rows;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
             const int col_base = n_blk * p.bn_main;
+            if (half < n_groups) prefetch(row, row_ok, col_base + half * ppg * 32);   // overlaps the wait for the accumulator
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
             float inv_den = 1.f;
             if (p.epi == SGF_EPI_ATTN_APPLY) {
                 float t[16];
@@ -275,18 +398,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             const float rs = (p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
             const float r1r = (p.r1_row && row_ok) ? p.r1_row[row] : 0.f;
             // -------- 32-column pieces; piece index pc covers tile columns [32*pc, 32*pc+32) --------
-            const int n_pieces = (p.bn_main + 31) / 32;
-            const int ppg = GW / 32;                                   // pieces per staging group (bf16: 2, fp32: 1)
-            const int n_groups = (n_pieces + ppg - 1) / ppg;
             for (int g = half; g < n_groups; g += 2) {
-                const uint32_t buf = gcount & 1;
+                const uint32_t buf = stg_per_half == 2 ? (gcount & 1) : 0;
                 if (p.tma_store) {
-                    if (issuer) bulk_wait_read<1>();                   // the store that last used this buffer has drained
+                    if (issuer) {                                      // the store that last used this buffer has drained
+                        if (stg_per_half == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                    }
                     named_bar_sync(1 + half, 128);
                 }
                 for (int pp = 0; pp < ppg; ++pp) {
                     const int pc = g * ppg + pp;
                     if (pc >= n_pieces) break;
+                    // take this piece's prefetched addend, then put the next piece's in flight before touching TMEM
+                    uint4 cur[4];      // kept packed until it is used
+                    const bool have_ad = pre_ok;
+                    if (have_ad) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) cur[c] = pre[c];
+                    }
+                    {
+                        int next_pc = -1;
+                        if (pp + 1 < ppg && pc + 1 < n_pieces) next_pc = pc + 1;
+                        else if (g + 2 < n_groups) next_pc = (g + 2) * ppg;
+                        if (next_pc >= 0) prefetch(row, row_ok, col_base + next_pc * 32); else pre_ok = false;
+                    }
                     float v[32];
                     __syncwarp();  // tcgen05.ld is .sync.aligned
                     tmem_ld32(taddr + pc * 32, v);
@@ -295,61 +430,62 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                     const int ncol = p.n_out - col0 < 32 ? p.n_out - col0 : 32;   // valid columns of this piece (may be <= 0)
                     const bool full32 = ncol == 32;
                     if (row_ok && ncol > 0) {
-                        float ax[32];
-                        if (p.aux) {
-                            if (full32 && aux_vec_ok) { load16(p.aux, p.aux_dtype, row * p.ld_aux + col0, ax); load16(p.aux, p.aux_dtype, row * p.ld_aux + col0 + 16, ax + 16); }
-                            else
+                        // 8-column chunks: the addend is unpacked chunk by chunk so that at most v[32] + two packed addend
+                        // pieces are live (the kernel sits at the 168-register limit of 10 warps per CTA)
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) ax[j] = j < ncol ? load1(p.aux, p.aux_dtype, row * p.ld_aux + col0 + j) : 0.f;
-                        }
-                        if (p.epi == SGF_EPI_ATTN_APPLY) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= alpha;
-                            if (p.aux)
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] += beta * ax[j];
-                            if (p.bias) {
-                                if (full32 && vecf_ok && (col0 & 3) == 0) {
-                                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) { float4 b4 = __ldg(bp + j); v[4*j] += b4.x; v[4*j+1] += b4.y; v[4*j+2] += b4.z; v[4*j+3] += b4.w; }
-                                } else
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += p.bias[col0 + j];
+                        for (int c = 0; c < 4; ++c) {
+                            float* vc = v + 8 * c;
+                            const int colc = col0 + 8 * c;
+                            const int nv = ncol - 8 * c;                 // valid columns of this chunk (may be <= 0)
+                            if (nv <= 0) break;
+                            const bool full8 = nv >= 8;
+                            float a8[8];
+                            if (p.aux) {
+                                if (have_ad) Vec16<__nv_bfloat16>::unpack(cur[c], a8);
+                                else load8(p.aux, p.aux_dtype, row * p.ld_aux + colc, full8 && aux_vec_ok, nv, a8);
                             }
-                            if (p.r1_row) {
-                                if (full32 && vecf_ok && (col0 & 3) == 0) {
-                                    const float4* cp = reinterpret_cast<const float4*>(p.r1_col + col0);
+                            if (p.epi == SGF_EPI_ATTN_APPLY) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) { float4 c4 = __ldg(cp + j); v[4*j] += r1r * c4.x; v[4*j+1] += r1r * c4.y; v[4*j+2] += r1r * c4.z; v[4*j+3] += r1r * c4.w; }
-                                } else
+                                for (int j = 0; j < 8; ++j) vc[j] = (vc[j] + p.nf * a8[j]) * inv_den;
+                            } else {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += r1r * p.r1_col[col0 + j];
+                                for (int j = 0; j < 8; ++j) vc[j] *= alpha;
+                                if (p.aux)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) vc[j] += beta * a8[j];
+                                if (p.bias) {
+                                    if (full8 && vecf_ok && (colc & 3) == 0) {
+                                        const float4* bp = reinterpret_cast<const float4*>(p.bias + colc);
+#pragma unroll
+                                        for (int j = 0; j < 2; ++j) { float4 b4 = __ldg(bp + j); vc[4*j] += b4.x; vc[4*j+1] += b4.y; vc[4*j+2] += b4.z; vc[4*j+3] += b4.w; }
+                                    } else
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) if (j < nv) vc[j] += p.bias[colc + j];
+                                }
+                                if (p.r1_row) {
+                                    if (full8 && vecf_ok && (colc & 3) == 0) {
+                                        const float4* cp = reinterpret_cast<const float4*>(p.r1_col + colc);
+#pragma unroll
+                                        for (int j = 0; j < 2; ++j) { float4 c4 = __ldg(cp + j); vc[4*j] += r1r * c4.x; vc[4*j+1] += r1r * c4.y; vc[4*j+2] += r1r * c4.z; vc[4*j+3] += r1r * c4.w; }
+                                    } else
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) if (j < nv) vc[j] += r1r * p.r1_col[colc + j];
+                                }
+                                if (p.relu)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) vc[j] = fmaxf(vc[j], 0.f);
+                                if (p.row_scale)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) vc[j] *= rs;
                             }
-                            if (p.relu)
+                            if (p.accumulate) {
+                                float o8[8];
+                                if (have_ad && !p.aux) Vec16<__nv_bfloat16>::unpack(cur[c], o8);
+                                else load8(p.out, p.out_dtype, row * p.ldo + colc, full8 && vec_ok, nv, o8);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                            if (p.row_scale)
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= rs;
-                        }
-                        if (p.accumulate) {
-                            float old[32];
-                            if (full32 && vec_ok) { load16(p.out, p.out_dtype, row * p.ldo + col0, old); load16(p.out, p.out_dtype, row * p.ldo + col0 + 16, old + 16); }
-                            else
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) old[j] = j < ncol ? load1(p.out, p.out_dtype, row * p.ldo + col0 + j) : 0.f;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += old[j];
-                        }
-                        if (!p.tma_store) {
-                            if (full32 && vec_ok) { store16(p.out, p.out_dtype, row * p.ldo + col0, v); store16(p.out, p.out_dtype, row * p.ldo + col0 + 16, v + 16); }
-                            else
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) if (j < ncol) store1(p.out, p.out_dtype, row * p.ldo + col0 + j, v[j]);
+                                for (int j = 0; j < 8; ++j) vc[j] += o8[j];
+                            }
+                            if (!p.tma_store) store8(p.out, p.out_dtype, row * p.ldo + colc, full8 && vec_ok, nv, vc);
                         }
                     }
                     if (p.tma_store) {
@@ -617,6 +753,14 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
         p.seg[s].k_blocks = (klen + nt::BK - 1) / nt::BK;
         p.total_kb += p.seg[s].k_blocks;
     }
+    // explicit resident-B request: narrow the n-blocks until one block of B fits (A is then re-read from L2 per n-block)
+    if (a->schedule == SGF_GEMM_RESIDENT_B && !has_tail) {
+        while ((int64_t)p.bn_main * nt::BK * 2 * p.total_kb > nt::RES_BYTES && p.bn_main > 16) {
+            ++p.n_blocks;
+            p.bn_main = ((n16 / 16 + p.n_blocks - 1) / p.n_blocks) * 16;
+        }
+        p.num_tiles = m_blocks * p.n_blocks;
+    }
     int rc;
     for (int i = 0; i < a->n_a; ++i)
         if ((rc = make_tmap_bf16(&tm.a[i], a->a[i], a->rows, a->a_cols[i], a->lda[i], nt::BM))) return rc;
@@ -641,13 +785,27 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
         if ((p.col_sum || p.col_sumsq) && (!p.tma_store || a->n_out > nt::STAT_COLS)) return SGF_ERR_UNSUPPORTED;
     }
 
+    // resident-B schedule whenever one n-block of B (all k-blocks) fits: see nt::RES_BYTES
+    {
+        const int64_t b_tx = (int64_t)(p.bn_main + (has_tail ? 16 : 0)) * nt::BK * 2;
+        const bool fits = p.total_kb <= nt::RES_MAX_KB && b_tx * p.total_kb <= nt::RES_BYTES;
+        if (a->schedule == SGF_GEMM_RESIDENT_B && !fits) return SGF_ERR_UNSUPPORTED;
+        p.b_res = (a->schedule != SGF_GEMM_STREAM_B && fits) ? 1 : 0;
+        // several n-blocks: B is re-loaded per (chunk, n-block); a chunk of 8 row tiles per CTA keeps the A tiles that are
+        // re-read for the following n-blocks inside L2 (148 CTAs x 8 x 128 rows x K x 2 B = 75 MB at K = 256)
+        p.chunk = p.n_blocks == 1 ? (int64_t)1 << 40 : 8;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        SGF_CUDA_TRY(cudaFuncSetAttribute(nt::gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt::SMEM_BYTES));
+        const int smem_max = nt::SMEM_BYTES > nt::SMEM_BYTES_RES ? nt::SMEM_BYTES : nt::SMEM_BYTES_RES;
+        SGF_CUDA_TRY(cudaFuncSetAttribute(nt::gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         attr_set = true;
     }
-    int64_t grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    nt::gemm_nt_kernel<<<(unsigned)grid, nt::THREADS, nt::SMEM_BYTES, (cudaStream_t)stream>>>(tm, p);
+    // resident-B: one CTA per SM over ROW tiles (every CTA visits all n-blocks of its rows)
+    const int64_t work = p.b_res ? m_blocks : p.num_tiles;
+    int64_t grid = work < num_sms() ? work : num_sms();
+    const int smem_bytes = p.b_res ? nt::SMEM_BYTES_RES : nt::SMEM_BYTES;
+    nt::gemm_nt_kernel<<<(unsigned)grid, nt::THREADS, smem_bytes, (cudaStream_t)stream>>>(tm, p);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

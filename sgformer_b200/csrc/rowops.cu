@@ -141,8 +141,12 @@ __device__ __forceinline__ void flush_columns(const Lane<T, CPL>& L, float (&acc
 #define SGF_FOR_ELEMS _Pragma("unroll") for (int c = 0; c < CPL; ++c) _Pragma("unroll") for (int i = 0; i < VN; ++i)
 
 // ------------------------------------------------------------------------------------------------
+// rows in flight per lane group / live registers of the colstats loop (packed loads + two fp32 accumulator sets)
+template <typename T, int CPL> __host__ __device__ constexpr int colstats_unroll() { return CPL * Vec16<T>::N <= 8 ? 4 : 2; }
+template <typename T, int CPL> __host__ __device__ constexpr int colstats_live() { return colstats_unroll<T, CPL>() * CPL * 4 + 2 * CPL * Vec16<T>::N; }
+
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kRowBlock, 3) colstats_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int h, int chunks,
+__global__ void __launch_bounds__(kRowBlock, (colstats_live<T, CPL>() > 56 ? 2 : 3)) colstats_kernel(const T* __restrict__ x, int64_t ldx, int64_t rows, int h, int chunks,
                                                               int lpr_log2, const float* __restrict__ w, float* __restrict__ sum,
                                                               float* __restrict__ sumsq) {
     constexpr int VN = Vec16<T>::N;
@@ -150,8 +154,9 @@ __global__ void __launch_bounds__(kRowBlock, 3) colstats_kernel(const T* __restr
     Lane<T, CPL> L(chunks, lpr_log2);
     float s1[CPL][VN], s2[CPL][VN];
     SGF_ZERO(s1) SGF_ZERO(s2)
-    // four rows in flight per lane group (packed) before the accumulation: a pure reduction has no other latency hiding
-    constexpr int U = 4;
+    // 2-4 rows in flight per lane group (packed) before the accumulation: a pure reduction has no other latency hiding.
+    // Wide rows (> 56 live registers of loads + accumulators) run 2 CTAs/SM so that U = 2 does not spill.
+    constexpr int U = colstats_unroll<T, CPL>();
 #pragma unroll 1
     for (int64_t r = L.row0; r < rows; r += U * L.row_step) {
         uint4 raw[U][CPL];

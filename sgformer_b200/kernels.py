@@ -287,7 +287,7 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
             alpha_dev: Optional[Tensor] = None, beta_dev: Optional[Tensor] = None, relu: bool = False,
             accumulate: bool = False, tail: Optional[Operand] = None, nf: float = 0.0, den_out: Optional[Tensor] = None,
             r1_row: Optional[Tensor] = None, r1_col: Optional[Tensor] = None, col_sum: Optional[Tensor] = None,
-            col_sumsq: Optional[Tensor] = None) -> Tensor:
+            col_sumsq: Optional[Tensor] = None, schedule: Optional[int] = None) -> Tensor:
     """out[rows, n_out] = epilogue(sum over `pairs` (ai, a_k0, bi, b_k0, klen) of A[ai][:, a_k0:+klen] . B[bi][:, b_k0:+klen]^T).
 
     Logical K offsets; 3-plane operands expand every pair into the six bf16x3 partial products."""
@@ -343,6 +343,7 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
     fused_stats = (col_sum is not None or col_sumsq is not None) and stats_fusable(out)
     if fused_stats:
         args.col_sum, args.col_sumsq = _p(_f32vec(col_sum, n_out, "col_sum")), _p(_f32vec(col_sumsq, n_out, "col_sumsq"))
+    args.schedule = GEMM_NT_SCHEDULE if schedule is None else schedule
     check(lib().sgf_gemm_nt(C.byref(args), _stream()), "sgf_gemm_nt")
     if (col_sum is not None or col_sumsq is not None) and not fused_stats:
         s_, q_ = colstats(out, want_sum=col_sum is not None, want_sumsq=col_sumsq is not None)   # unaligned output: extra pass
@@ -352,6 +353,9 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
             col_sumsq.add_(q_)
     return out
 
+
+# 0 auto / 1 stream B through the TMA ring / 2 B resident in shared memory (include/sgformer_b200.h: sgf_gemm_nt_args.schedule)
+GEMM_NT_SCHEDULE = int(os.environ.get("SGF_GEMM_NT_SCHEDULE", "0"))
 
 # Measured on B200 (products shape): accumulating the statistics in the GEMM epilogue costs more epilogue issue slots than the
 # separate 0.31 ms colstats pass it saves (105.3 vs 101.4 ms/step), so the fused path is opt-in.

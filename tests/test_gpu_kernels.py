@@ -388,6 +388,34 @@ def test_gemm_nt_fused_column_stats(K, monkeypatch, rows, k, n_out, dtype):
     _close(cs, out.float().sum(0), 1e-4, 1e-2, "vs torch sum")
 
 
+@pytest.mark.parametrize("rows,k,n_out", [(200_000, 64, 600), (160_001, 128, 256), (4100, 256, 768), (3000, 512, 256), (130, 256, 48)])
+def test_gemm_nt_schedules_agree(K, rows, k, n_out):
+    """Resident-B (weights parked in shared memory, row tiles visited in chunks with the n-block loop outside) and the
+    streaming schedule issue the same MMAs per tile: outputs must be bit-identical, including the prefetched bf16 addend
+    (aux / accumulate) of the epilogue.  200 k rows = more than 8 row tiles per CTA, i.e. several chunks per CTA."""
+    g = torch.Generator().manual_seed(rows + n_out)
+    a = torch.randn(rows, k, generator=g).to(DEV)
+    b = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(DEV)
+    bias = torch.randn(n_out, generator=g).to(DEV)
+    aux = torch.randn(rows, n_out, generator=g).to(DEV).to(torch.bfloat16)
+    A, B = K.pack_operand(a, False, 1), K.pack_operand(b, False, 1)
+    outs = {}
+    for sched in (1, 2):
+        o1 = K.alloc_act(rows, n_out, torch.bfloat16, DEV)
+        K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, o1, bias=bias, schedule=sched)
+        o2 = K.alloc_act(rows, n_out, torch.bfloat16, DEV)
+        K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, o2, aux=aux, beta=0.5, alpha=2.0, schedule=sched)
+        o3 = aux.clone()
+        K.gemm_nt([A], [B], [(0, 0, 0, 0, k)], n_out, o3, accumulate=True, relu=True, schedule=sched)
+        outs[sched] = (o1, o2, o3)
+    for x, y, what in zip(outs[1], outs[2], ("bias", "aux", "accumulate")):
+        assert torch.equal(x, y), f"schedules differ ({what}): max diff {(x.float() - y.float()).abs().max().item()}"
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    _close(outs[2][0].float(), ref + bias, 2e-2, 2e-2, "resident vs matmul")
+    _close(outs[2][1].float(), 2.0 * ref + 0.5 * aux.float(), 3e-2, 2e-2, "resident aux vs matmul")
+    _close(outs[2][2].float(), torch.relu(ref) + aux.float(), 2e-2, 2e-2, "resident accumulate vs matmul")
+
+
 @pytest.mark.parametrize("planes", [1, 3])
 @pytest.mark.parametrize("h", [16, 32, 64, 256])
 def test_gemm_nt_concat_segments(K, planes, h):

@@ -306,3 +306,30 @@ def test_reference_plumbing_methods():
     with pytest.raises(ValueError):
         L.SGFormer(16, 32, 5, aggregate="sum")
     assert model.get_attentions is not None and print(model) is None
+
+
+def test_host_feeder_double_buffering():
+    """HostFeeder hands out exactly what was submitted, in order, while the next submit overwrites the other slot."""
+    from sgformer_b200.feed import HostFeeder
+    dev = torch.device("cuda:0")
+    feeder = HostFeeder(dev)
+    host = [(torch.full((1 << 20,), float(i)).pin_memory(), torch.arange(i, i + 1000).pin_memory()) for i in range(6)]
+    feeder.submit(host[0])
+    with pytest.raises(RuntimeError):
+        feeder.submit(host[1])          # one slot belongs to the consumer: only one submit may be outstanding with 2 slots
+    sums = []
+    for i in range(6):
+        a, b = feeder.get()
+        if i + 1 < 6:
+            feeder.submit(host[i + 1])
+        # a long-ish consumer on the compute stream: the following submit must not overwrite its inputs early
+        acc = a.clone()
+        for _ in range(20):
+            acc = acc * 1.0 + 0.0
+        sums.append((acc.sum(), b.sum()))
+    torch.cuda.synchronize()
+    for i, (sa, sb) in enumerate(sums):
+        assert sa.item() == float(i) * (1 << 20)
+        assert sb.item() == sum(range(i, i + 1000))
+    with pytest.raises(RuntimeError):
+        feeder.get()
