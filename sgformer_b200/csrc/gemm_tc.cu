@@ -734,8 +734,11 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     // a 16-column tail needs n-block + 16 <= 256 TMEM columns per accumulator stage to keep the two stages (MMA of tile i+1
     // overlapping the epilogue of tile i): split a 256-wide output into two 128(+16) blocks (the tail is recomputed, cheap)
     if (has_tail && n16 + 16 > 256) p.n_blocks = 2;
-    // equal-width n-blocks, each a multiple of 16
-    p.bn_main = ((n16 / 16 + p.n_blocks - 1) / p.n_blocks) * 16;
+    // equal-width n-blocks: a multiple of 16 (UMMA N), and of 64 when there are several - the epilogue stores 128-byte
+    // groups (64 bf16 / 32 fp32 columns), which must not reach into the next n-block's columns
+    p.bn_main = p.n_blocks == 1 ? n16 : ((n16 / p.n_blocks + 63) / 64) * 64;
+    if (p.bn_main > 256) return SGF_ERR_UNSUPPORTED;
+    p.n_blocks = (n16 + p.bn_main - 1) / p.bn_main;
     p.has_tail = has_tail ? 1 : 0;
     const int64_t m_blocks = (a->rows + nt::BM - 1) / nt::BM;
     p.num_tiles = m_blocks * p.n_blocks;
@@ -755,9 +758,9 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     }
     // explicit resident-B request: narrow the n-blocks until one block of B fits (A is then re-read from L2 per n-block)
     if (a->schedule == SGF_GEMM_RESIDENT_B && !has_tail) {
-        while ((int64_t)p.bn_main * nt::BK * 2 * p.total_kb > nt::RES_BYTES && p.bn_main > 16) {
-            ++p.n_blocks;
-            p.bn_main = ((n16 / 16 + p.n_blocks - 1) / p.n_blocks) * 16;
+        while ((int64_t)p.bn_main * nt::BK * 2 * p.total_kb > nt::RES_BYTES && p.bn_main > 64) {
+            p.bn_main -= 64;
+            p.n_blocks = (n16 + p.bn_main - 1) / p.bn_main;
         }
         p.num_tiles = m_blocks * p.n_blocks;
     }
@@ -790,7 +793,9 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
         const int64_t b_tx = (int64_t)(p.bn_main + (has_tail ? 16 : 0)) * nt::BK * 2;
         const bool fits = p.total_kb <= nt::RES_MAX_KB && b_tx * p.total_kb <= nt::RES_BYTES;
         if (a->schedule == SGF_GEMM_RESIDENT_B && !fits) return SGF_ERR_UNSUPPORTED;
-        p.b_res = (a->schedule != SGF_GEMM_STREAM_B && fits) ? 1 : 0;
+        // AUTO = streaming: on B200 the resident schedule needs the staging tiles' shared memory for B, and the exposed TMA-store
+        // drain of a single staging buffer per epilogue half costs more than the L2 traffic it saves (r1c A/B)
+        p.b_res = (a->schedule == SGF_GEMM_RESIDENT_B && fits) ? 1 : 0;
         // several n-blocks: B is re-loaded per (chunk, n-block); a chunk of 8 row tiles per CTA keeps the A tiles that are
         // re-read for the following n-blocks inside L2 (148 CTAs x 8 x 128 rows x K x 2 B = 75 MB at K = 256)
         p.chunk = p.n_blocks == 1 ? (int64_t)1 << 40 : 8;
