@@ -16,6 +16,7 @@
 #include "launch_count.h"
 #include "../../include/sgformer_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -71,7 +72,8 @@ constexpr int THREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, war
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES_MAX = (256 + 16) * BK * 2;  // 34 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
-constexpr int STG_BYTES = BM * 128;               // output staging tile: 128 rows x 128 bytes (SW128), 2 per epilogue half
+constexpr int STG_BYTES = BM * 128;               // output staging: 128 rows x 128 bytes (SW128) = one 4 KB tile per epilogue warp ...
+constexpr int WSTG_BYTES = 32 * 128;              // ... of 32 rows (its TMEM lane quadrant), stored by the warp's own TMA store
 constexpr int BAR_BYTES = 512;
 constexpr int STAT_COLS = 1024;                   // fused column statistics cover n_out <= 1024
 constexpr int STAT_BYTES = 2 * STAT_COLS * 4;
@@ -123,6 +125,39 @@ __device__ __forceinline__ float load1(const void* base, int dtype, int64_t off)
 __device__ __forceinline__ void store1(void* base, int dtype, int64_t off, float v) {
     if (dtype == 1) static_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
     else static_cast<float*>(base)[off] = v;
+}
+// 32 consecutive elements at element offset `off` (vec: 16-byte aligned and all 32 valid; else the first nv, rest 0)
+__device__ __forceinline__ void load32(const void* base, int dtype, int64_t off, bool vec, int nv, float* f) {
+    if (vec) {
+        if (dtype == 1) {
+            const uint4* q = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Vec16<__nv_bfloat16>::unpack(q[i], f + 8 * i);
+        } else {
+            const uint4* q = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Vec16<float>::unpack(q[i], f + 4 * i);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = j < nv ? load1(base, dtype, off + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void store32(void* base, int dtype, int64_t off, bool vec, int nv, const float* f) {
+    if (vec) {
+        if (dtype == 1) {
+            uint4* q = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = Vec16<__nv_bfloat16>::pack(f + 8 * i);
+        } else {
+            uint4* q = reinterpret_cast<uint4*>(static_cast<float*>(base) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = Vec16<float>::pack(f + 4 * i);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < nv) store1(base, dtype, off + j, f[j]);
+    }
 }
 // 8 consecutive elements starting at element offset `off` (vec: 16-byte aligned and all 8 valid; else the first nv, rest 0)
 __device__ __forceinline__ void load8(const void* base, int dtype, int64_t off, bool vec, int nv, float* f) {
@@ -208,6 +243,12 @@ struct TileIter {
     }
 };
 
+// Epilogue feature bits.  A specialised instantiation gemm_nt_kernel<F> compiles exactly the features in F (present and
+// unconditional: bf16 output through the TMA-store path, every 32-column piece complete, bf16 16-byte-aligned addends); the
+// F_GENERIC instantiation reads every feature from Params at run time and handles ragged widths, fp32 and unaligned tensors.
+enum : int { F_BIAS = 1, F_AUX = 2, F_RELU = 4, F_ROWSCALE = 8, F_ACCUM = 16, F_R1 = 32, F_ATTN = 64, F_GENERIC = 128 };
+
+template <int F>
 __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ Tmaps tm, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -217,9 +258,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     uint8_t* ring = res ? smem + RES_BYTES : smem;
     const int ring_stages = res ? RES_STAGES : STAGES;
     const int ring_stride = res ? A_BYTES : STAGE_BYTES;
-    const int stg_per_half = res ? RES_STG / 2 : 2;
+    const int stg_per_warp = res ? 1 : 2;                 // warp-private [32 rows x 128 B] staging tiles
     uint8_t* staging = ring + ring_stages * ring_stride;
-    uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * stg_per_half * STG_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * stg_per_warp * WSTG_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -336,36 +377,49 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> (smem staging -> TMA store | direct global stores) =====
+        // ===== epilogue: TMEM -> registers -> (warp-private smem staging -> TMA store | direct global stores) =====
+        // Each warp owns the 32 rows of its TMEM lane quadrant and every other 128-byte column group (two warps per
+        // quadrant), stages a [32 x 128 B] tile and stores it with its own TMA store: no cross-warp synchronisation.
+        constexpr bool GEN = (F & F_GENERIC) != 0;
+        const bool f_bias = GEN ? p.bias != nullptr : (F & F_BIAS) != 0;
+        const bool f_aux = GEN ? p.aux != nullptr : (F & F_AUX) != 0;
+        const bool f_relu = GEN ? p.relu != 0 : (F & F_RELU) != 0;
+        const bool f_rs = GEN ? p.row_scale != nullptr : (F & F_ROWSCALE) != 0;
+        const bool f_acc = GEN ? p.accumulate != 0 : (F & F_ACCUM) != 0;
+        const bool f_r1 = GEN ? p.r1_row != nullptr : (F & F_R1) != 0;
+        const bool f_attn = GEN ? p.epi == SGF_EPI_ATTN_APPLY : (F & F_ATTN) != 0;
+        const bool f_tma = GEN ? p.tma_store != 0 : true;
+        const bool f_stats = GEN ? want_stats : false;
+        const int out_dtype = GEN ? p.out_dtype : 1;
         const int ew = warp - 2;     // 0..7
         const int q = warp & 3;      // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;    // the two halves alternate over column groups
+        const int half = ew >> 2;    // the two warps of a quadrant alternate over column groups
         float alpha = p.alpha, beta = p.beta;
         if (p.alpha_dev) alpha *= *p.alpha_dev;
         if (p.beta_dev) beta *= *p.beta_dev;
-        const int out_es = p.out_dtype == 1 ? 2 : 4, aux_es = p.aux_dtype == 1 ? 2 : 4;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.ldo * out_es) % 16 == 0);
-        const bool aux_vec_ok = !p.aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ld_aux * aux_es) % 16 == 0));
-        const bool vecf_ok = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
-                             (!p.r1_col || (reinterpret_cast<uintptr_t>(p.r1_col) & 15) == 0);
-        const int GW = p.out_dtype == 1 ? 64 : 32;            // columns per 128-byte staging row
-        uint8_t* stg = staging + half * stg_per_half * STG_BYTES;
-        const bool issuer = ((ew & 3) == 0) && lane == 0;    // one TMA-store issuing thread per half
+        const int out_es = out_dtype == 1 ? 2 : 4, aux_es = p.aux_dtype == 1 ? 2 : 4;
+        const bool vec_ok = !GEN || (((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.ldo * out_es) % 16 == 0));
+        const bool aux_vec_ok = !GEN || !p.aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && ((p.ld_aux * aux_es) % 16 == 0));
+        const bool vecf_ok = !GEN || ((!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                                      (!p.r1_col || (reinterpret_cast<uintptr_t>(p.r1_col) & 15) == 0));
+        const int GW = out_dtype == 1 ? 64 : 32;              // columns per 128-byte staging row
+        uint8_t* wstg = staging + ew * stg_per_warp * WSTG_BYTES;
         const int r_local = q * 32 + lane;
         // The addend of the epilogue (aux, else the old output when accumulating) is fetched one 32-column piece AHEAD as
-        // packed 16-byte chunks: a thread owns a whole row, so an un-prefetched load costs a full DRAM latency per piece
-        // (r1b: GEMMs with aux/accumulate ran 2x slower than those without).  16-bit sources only (4 registers / 32 columns... x4).
-        const void* pre_src = p.aux ? p.aux : (p.accumulate ? p.out : nullptr);
-        const int64_t pre_ld = p.aux ? p.ld_aux : p.ldo;
-        const bool pre_on = pre_src && (p.aux ? p.aux_dtype == 1 && aux_vec_ok : p.out_dtype == 1 && vec_ok);
+        // packed 16-byte chunks: a thread owns a whole row, so an un-prefetched load costs a DRAM latency per piece.
+        const void* pre_src = f_aux ? p.aux : (f_acc ? p.out : nullptr);
+        const int64_t pre_ld = f_aux ? p.ld_aux : p.ldo;
+        const bool pre_on = GEN ? (pre_src && (f_aux ? p.aux_dtype == 1 && aux_vec_ok : out_dtype == 1 && vec_ok)) : (f_aux || f_acc);
         uint4 pre[4];
         bool pre_ok = false;     // pre[] holds the addend of the NEXT piece to be processed
         auto prefetch = [&](int64_t row, bool row_ok, int col0) {
-            pre_ok = pre_on && row_ok && col0 + 32 <= p.n_out;
+            pre_ok = pre_on && row_ok && (!GEN || col0 + 32 <= p.n_out);
             if (pre_ok) {
                 const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(pre_src) + row * pre_ld + col0);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) pre[c] = p.aux ? ldg_nc_na(src + c) : src[c];
+                // L1-allocating loads: a thread reads its row 64 bytes at a time, the second half of each 128-byte line
+                // must hit L1 (ld.global.nc.L1::no_allocate here made the addend GEMMs 1.5x slower than r1b)
+                for (int c = 0; c < 4; ++c) pre[c] = f_aux ? __ldg(src + c) : src[c];
             }
         };
         const int n_pieces = (p.bn_main + 31) / 32;
@@ -382,11 +436,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             const bool row_ok = row < p.rows;
             const int col_base = n_blk * p.bn_main;
             if (half < n_groups) prefetch(row, row_ok, col_base + half * ppg * 32);   // overlaps the wait for the accumulator
+            const float rs = (f_rs && row_ok) ? p.row_scale[row] : 1.f;
+            const float r1r = (f_r1 && row_ok) ? p.r1_row[row] : 0.f;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
             float inv_den = 1.f;
-            if (p.epi == SGF_EPI_ATTN_APPLY) {
+            if (f_attn) {
                 float t[16];
                 __syncwarp();
                 tmem_ld16(taddr + p.bn_main, t);
@@ -395,22 +451,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                 inv_den = 1.f / den;
                 if (row_ok && p.den_out && half == 0 && n_blk == 0) p.den_out[row] = den;
             }
-            const float rs = (p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
-            const float r1r = (p.r1_row && row_ok) ? p.r1_row[row] : 0.f;
             // -------- 32-column pieces; piece index pc covers tile columns [32*pc, 32*pc+32) --------
             for (int g = half; g < n_groups; g += 2) {
-                const uint32_t buf = stg_per_half == 2 ? (gcount & 1) : 0;
-                if (p.tma_store) {
-                    if (issuer) {                                      // the store that last used this buffer has drained
-                        if (stg_per_half == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                const uint32_t buf = stg_per_warp == 2 ? (gcount & 1) : 0;
+                if (f_tma) {
+                    if (lane == 0) {                                   // the store that last used this buffer has drained
+                        if (stg_per_warp == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                     }
-                    named_bar_sync(1 + half, 128);
+                    __syncwarp();
                 }
                 for (int pp = 0; pp < ppg; ++pp) {
                     const int pc = g * ppg + pp;
                     if (pc >= n_pieces) break;
-                    // take this piece's prefetched addend, then put the next piece's in flight before touching TMEM
-                    uint4 cur[4];      // kept packed until it is used
+                    // take this piece's prefetched addend (kept packed), then put the next piece's in flight
+                    uint4 cur[4];
                     const bool have_ad = pre_ok;
                     if (have_ad) {
 #pragma unroll
@@ -427,114 +481,136 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                     tmem_ld32(taddr + pc * 32, v);
                     tmem_ld_wait();
                     const int col0 = col_base + pc * 32;
-                    const int ncol = p.n_out - col0 < 32 ? p.n_out - col0 : 32;   // valid columns of this piece (may be <= 0)
+                    const int ncol = GEN ? (p.n_out - col0 < 32 ? p.n_out - col0 : 32) : 32;   // valid columns (may be <= 0)
                     const bool full32 = ncol == 32;
                     if (row_ok && ncol > 0) {
-                        // 8-column chunks: the addend is unpacked chunk by chunk so that at most v[32] + two packed addend
-                        // pieces are live (the kernel sits at the 168-register limit of 10 warps per CTA)
+                        if (f_attn) {
+                            if (have_ad) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float* vc = v + 8 * c;
-                            const int colc = col0 + 8 * c;
-                            const int nv = ncol - 8 * c;                 // valid columns of this chunk (may be <= 0)
-                            if (nv <= 0) break;
-                            const bool full8 = nv >= 8;
-                            float a8[8];
-                            if (p.aux) {
-                                if (have_ad) Vec16<__nv_bfloat16>::unpack(cur[c], a8);
-                                else load8(p.aux, p.aux_dtype, row * p.ld_aux + colc, full8 && aux_vec_ok, nv, a8);
-                            }
-                            if (p.epi == SGF_EPI_ATTN_APPLY) {
+                                for (int c = 0; c < 4; ++c) {
+                                    float a8[8];
+                                    Vec16<__nv_bfloat16>::unpack(cur[c], a8);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) vc[j] = (vc[j] + p.nf * a8[j]) * inv_den;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) vc[j] *= alpha;
-                                if (p.aux)
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) vc[j] += beta * a8[j];
-                                if (p.bias) {
-                                    if (full8 && vecf_ok && (colc & 3) == 0) {
-                                        const float4* bp = reinterpret_cast<const float4*>(p.bias + colc);
-#pragma unroll
-                                        for (int j = 0; j < 2; ++j) { float4 b4 = __ldg(bp + j); vc[4*j] += b4.x; vc[4*j+1] += b4.y; vc[4*j+2] += b4.z; vc[4*j+3] += b4.w; }
-                                    } else
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) if (j < nv) vc[j] += p.bias[colc + j];
+                                    for (int j = 0; j < 8; ++j) v[8 * c + j] = (v[8 * c + j] + p.nf * a8[j]) * inv_den;
                                 }
-                                if (p.r1_row) {
-                                    if (full8 && vecf_ok && (colc & 3) == 0) {
-                                        const float4* cp = reinterpret_cast<const float4*>(p.r1_col + colc);
+                            } else if constexpr (GEN) {
+                                float ax[32];
+                                load32(p.aux, p.aux_dtype, row * p.ld_aux + col0, full32 && aux_vec_ok, ncol, ax);
 #pragma unroll
-                                        for (int j = 0; j < 2; ++j) { float4 c4 = __ldg(cp + j); vc[4*j] += r1r * c4.x; vc[4*j+1] += r1r * c4.y; vc[4*j+2] += r1r * c4.z; vc[4*j+3] += r1r * c4.w; }
-                                    } else
+                                for (int j = 0; j < 32; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
+                            }
+                        } else {
 #pragma unroll
-                                        for (int j = 0; j < 8; ++j) if (j < nv) vc[j] += r1r * p.r1_col[colc + j];
+                            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+                            if (f_aux) {
+                                if (have_ad) {
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) {
+                                        float a8[8];
+                                        Vec16<__nv_bfloat16>::unpack(cur[c], a8);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[8 * c + j] += beta * a8[j];
+                                    }
+                                } else if constexpr (GEN) {
+                                    float ax[32];
+                                    load32(p.aux, p.aux_dtype, row * p.ld_aux + col0, full32 && aux_vec_ok, ncol, ax);
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] += beta * ax[j];
                                 }
-                                if (p.relu)
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) vc[j] = fmaxf(vc[j], 0.f);
-                                if (p.row_scale)
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) vc[j] *= rs;
                             }
-                            if (p.accumulate) {
-                                float o8[8];
-                                if (have_ad && !p.aux) Vec16<__nv_bfloat16>::unpack(cur[c], o8);
-                                else load8(p.out, p.out_dtype, row * p.ldo + colc, full8 && vec_ok, nv, o8);
+                            if (f_bias) {
+                                if (!GEN || (full32 && vecf_ok && (col0 & 3) == 0)) {
+                                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) vc[j] += o8[j];
+                                    for (int j = 0; j < 8; ++j) { float4 b4 = __ldg(bp + j); v[4*j] += b4.x; v[4*j+1] += b4.y; v[4*j+2] += b4.z; v[4*j+3] += b4.w; }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += p.bias[col0 + j];
+                                }
                             }
-                            if (!p.tma_store) store8(p.out, p.out_dtype, row * p.ldo + colc, full8 && vec_ok, nv, vc);
+                            if (f_r1) {
+                                if (!GEN || (full32 && vecf_ok && (col0 & 3) == 0)) {
+                                    const float4* cp = reinterpret_cast<const float4*>(p.r1_col + col0);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { float4 c4 = __ldg(cp + j); v[4*j] += r1r * c4.x; v[4*j+1] += r1r * c4.y; v[4*j+2] += r1r * c4.z; v[4*j+3] += r1r * c4.w; }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += r1r * p.r1_col[col0 + j];
+                                }
+                            }
+                            if (f_relu)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                            if (f_rs)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] *= rs;
+                        }
+                        if (f_acc) {
+                            if (have_ad && !f_aux) {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    float o8[8];
+                                    Vec16<__nv_bfloat16>::unpack(cur[c], o8);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[8 * c + j] += o8[j];
+                                }
+                            } else if (GEN || f_aux) {
+                                float old[32];
+                                load32(p.out, out_dtype, row * p.ldo + col0, full32 && vec_ok, ncol, old);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += old[j];
+                            }
+                        }
+                        if constexpr (GEN) {
+                            if (!f_tma) store32(p.out, out_dtype, row * p.ldo + col0, full32 && vec_ok, ncol, v);
                         }
                     }
-                    if (p.tma_store) {
+                    if (f_tma) {
                         // 128-byte staging row, 16-byte chunks XOR-swizzled with (row & 7) (== TMA SWIZZLE_128B); OOB rows/cols
                         // are clipped by the TMA store, so garbage there is harmless
-                        uint8_t* rowp = stg + buf * STG_BYTES + r_local * 128;
-                        if (p.out_dtype == 1) {
+                        uint8_t* rowp = wstg + buf * WSTG_BYTES + lane * 128;
+                        if (out_dtype == 1) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const int chunk = (pp * 4 + c) ^ (r_local & 7);
+                                const int chunk = (pp * 4 + c) ^ (lane & 7);
                                 *reinterpret_cast<uint4*>(rowp + chunk * 16) = Vec16<__nv_bfloat16>::pack(v + 8 * c);
                             }
                         } else {
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
-                                const int chunk = c ^ (r_local & 7);
+                                const int chunk = c ^ (lane & 7);
                                 *reinterpret_cast<uint4*>(rowp + chunk * 16) = Vec16<float>::pack(v + 4 * c);
                             }
                         }
                     }
                 }
-                if (p.tma_store) {
+                if (f_tma) {
                     fence_proxy_async_smem();
-                    named_bar_sync(1 + half, 128);
-                    if (issuer) {
-                        tma_store_2d(&tm.out, stg + buf * STG_BYTES, col_base + g * GW, m_blk * BM);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm.out, wstg + buf * WSTG_BYTES, col_base + g * GW, m_blk * BM + q * 32);
                         bulk_commit();
                     }
-                    if (want_stats) {
-                        // column sums of the staged (already rounded) tile: thread t of this half owns column t % GW and a
-                        // band of 128*GW/128 rows; the buffer is not rewritten before this half's next-but-one barrier
-                        const int th = (ew & 3) * 32 + lane;                  // 0..127 within the half
-                        const int cg = th % GW, band = th / GW, rows_band = BM / (128 / GW);
-                        const int colg = col_base + g * GW + cg;
-                        const int64_t valid_rows = p.rows - (int64_t)m_blk * BM;
-                        if (colg < p.n_out) {
-                            const uint8_t* tile = stg + buf * STG_BYTES;
+                    if (f_stats) {
+                        // column sums of the staged (already rounded) 32-row tile: lane l owns columns l (and l + 32 for bf16);
+                        // the buffer is rewritten only after this warp's next bulk_wait_read + __syncwarp
+                        const uint8_t* tile = wstg + buf * WSTG_BYTES;
+                        const int64_t valid_rows = p.rows - ((int64_t)m_blk * BM + q * 32);
+                        for (int cg = lane; cg < GW; cg += 32) {
+                            const int colg = col_base + g * GW + cg;
+                            if (colg >= p.n_out || colg >= col_base + p.bn_main) continue;
                             float s1 = 0.f, s2 = 0.f;
-                            for (int r = band * rows_band; r < (band + 1) * rows_band && r < valid_rows; ++r) {
-                                float v;
-                                if (p.out_dtype == 1) {
+                            for (int r = 0; r < 32 && r < valid_rows; ++r) {
+                                float x;
+                                if (out_dtype == 1) {
                                     const int chunk = (cg >> 3) ^ (r & 7);
-                                    v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + r * 128 + chunk * 16 + (cg & 7) * 2));
+                                    x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + r * 128 + chunk * 16 + (cg & 7) * 2));
                                 } else {
                                     const int chunk = (cg >> 2) ^ (r & 7);
-                                    v = *reinterpret_cast<const float*>(tile + r * 128 + chunk * 16 + (cg & 3) * 4);
+                                    x = *reinterpret_cast<const float*>(tile + r * 128 + chunk * 16 + (cg & 3) * 4);
                                 }
-                                s1 += v;
-                                s2 += v * v;
+                                s1 += x;
+                                s2 += x * x;
                             }
                             atomicAdd(&stat_sm[colg], s1);
                             atomicAdd(&stat_sm[STAT_COLS + colg], s2);
@@ -548,8 +624,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (p.tma_store && issuer) bulk_wait<0>();
-        if (want_stats) {
+        if (f_tma && lane == 0) bulk_wait<0>();
+        if (f_stats) {
             named_bar_sync(3, 32 * EPI_WARPS);
             for (int i = threadIdx.x - 64; i < p.n_out; i += 32 * EPI_WARPS) {
                 if (p.col_sum) atomicAdd(&p.col_sum[i], stat_sm[i]);
@@ -783,7 +859,7 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     {
         const int es = a->out_dtype == 1 ? 2 : 4;
         p.tma_store = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ldo * es) % 16 == 0) ? 1 : 0;
-        if (p.tma_store && (rc = make_tmap_2d(&tm.out, a->out, a->out_dtype, a->rows, a->n_out, a->ldo, nt::BM))) return rc;
+        if (p.tma_store && (rc = make_tmap_2d(&tm.out, a->out, a->out_dtype, a->rows, a->n_out, a->ldo, 32))) return rc;
         p.col_sum = a->col_sum; p.col_sumsq = a->col_sumsq;
         if ((p.col_sum || p.col_sumsq) && (!p.tma_store || a->n_out > nt::STAT_COLS)) return SGF_ERR_UNSUPPORTED;
     }
@@ -793,24 +869,62 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
         const int64_t b_tx = (int64_t)(p.bn_main + (has_tail ? 16 : 0)) * nt::BK * 2;
         const bool fits = p.total_kb <= nt::RES_MAX_KB && b_tx * p.total_kb <= nt::RES_BYTES;
         if (a->schedule == SGF_GEMM_RESIDENT_B && !fits) return SGF_ERR_UNSUPPORTED;
-        // AUTO = streaming: on B200 the resident schedule needs the staging tiles' shared memory for B, and the exposed TMA-store
-        // drain of a single staging buffer per epilogue half costs more than the L2 traffic it saves (r1c A/B)
-        p.b_res = (a->schedule == SGF_GEMM_RESIDENT_B && fits) ? 1 : 0;
+        // AUTO: resident when the whole B is one n-block (loaded once per CTA): same speed as streaming at K = 256 and 1.7x
+        // faster for short K (K = 100 -> 256: 0.32 vs 0.53 ms at 2.4 M rows), where a tile's few k-blocks cannot cover the TMA
+        // latency of re-fetching B.  With several n-blocks the per-chunk reload of B stalls the MMA (QKV 1.41 vs 1.15 ms).
+        p.b_res = (fits && (a->schedule == SGF_GEMM_RESIDENT_B || (a->schedule == SGF_GEMM_AUTO && p.n_blocks == 1))) ? 1 : 0;
         // several n-blocks: B is re-loaded per (chunk, n-block); a chunk of 8 row tiles per CTA keeps the A tiles that are
         // re-read for the following n-blocks inside L2 (148 CTAs x 8 x 128 rows x K x 2 B = 75 MB at K = 256)
         p.chunk = p.n_blocks == 1 ? (int64_t)1 << 40 : 8;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int smem_max = nt::SMEM_BYTES > nt::SMEM_BYTES_RES ? nt::SMEM_BYTES : nt::SMEM_BYTES_RES;
-        SGF_CUDA_TRY(cudaFuncSetAttribute(nt::gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        attr_set = true;
-    }
     // resident-B: one CTA per SM over ROW tiles (every CTA visits all n-blocks of its rows)
     const int64_t work = p.b_res ? m_blocks : p.num_tiles;
-    int64_t grid = work < num_sms() ? work : num_sms();
+    const int64_t grid = work < num_sms() ? work : num_sms();
     const int smem_bytes = p.b_res ? nt::SMEM_BYTES_RES : nt::SMEM_BYTES;
-    nt::gemm_nt_kernel<<<(unsigned)grid, nt::THREADS, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+
+    // epilogue specialisation: the exact feature set of this call if it has a compiled instantiation, else the generic kernel
+    int feat = (a->bias ? nt::F_BIAS : 0) | (a->aux ? nt::F_AUX : 0) | (a->relu ? nt::F_RELU : 0) |
+               (a->row_scale ? nt::F_ROWSCALE : 0) | (a->accumulate ? nt::F_ACCUM : 0) | (a->r1_row ? nt::F_R1 : 0) |
+               (a->epi == SGF_EPI_ATTN_APPLY ? nt::F_ATTN : 0);
+    const bool al16 = (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
+                      (!a->r1_col || (reinterpret_cast<uintptr_t>(a->r1_col) & 15) == 0) &&
+                      (!a->aux || (a->aux_dtype == 1 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && (a->ld_aux * 2) % 16 == 0));
+    const bool fast_ok = p.tma_store && a->out_dtype == 1 && a->n_out % 32 == 0 && al16 && !p.col_sum && !p.col_sumsq &&
+                         p.n_blocks * p.bn_main == a->n_out;     // every 32-column piece of every n-block is complete
+    static const bool no_special = [] { const char* e = getenv("SGF_GEMM_NT_GENERIC"); return e && e[0] == '1'; }();
+    if (!fast_ok || no_special) feat = nt::F_GENERIC;
+    const int smem_max = nt::SMEM_BYTES > nt::SMEM_BYTES_RES ? nt::SMEM_BYTES : nt::SMEM_BYTES_RES;
+#define SGF_NT_CASE(FEAT)                                                                                                   \
+    case (FEAT): {                                                                                                         \
+        static bool attr_set = false;                                                                                      \
+        if (!attr_set) {                                                                                                   \
+            SGF_CUDA_TRY(cudaFuncSetAttribute(nt::gemm_nt_kernel<(FEAT)>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                              smem_max));                                                                  \
+            attr_set = true;                                                                                               \
+        }                                                                                                                  \
+        nt::gemm_nt_kernel<(FEAT)><<<(unsigned)grid, nt::THREADS, smem_bytes, (cudaStream_t)stream>>>(tm, p);              \
+        launched = true;                                                                                                   \
+    } break;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        bool launched = false;
+        switch (feat) {
+            SGF_NT_CASE(0)
+            SGF_NT_CASE(nt::F_BIAS)
+            SGF_NT_CASE(nt::F_BIAS | nt::F_RELU)
+            SGF_NT_CASE(nt::F_ROWSCALE)
+            SGF_NT_CASE(nt::F_ACCUM)
+            SGF_NT_CASE(nt::F_AUX)
+            SGF_NT_CASE(nt::F_AUX | nt::F_ACCUM)
+            SGF_NT_CASE(nt::F_AUX | nt::F_BIAS)
+            SGF_NT_CASE(nt::F_AUX | nt::F_R1)
+            SGF_NT_CASE(nt::F_AUX | nt::F_ATTN)
+            SGF_NT_CASE(nt::F_GENERIC)
+            default: break;
+        }
+        if (launched) break;
+        feat = nt::F_GENERIC;     // no instantiation for this feature set
+    }
+#undef SGF_NT_CASE
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }
