@@ -11,12 +11,17 @@ replicated, and the schedule exchanges only
 through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  `Comm(None)` is the single-GPU no-op."""
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 Tensor = torch.Tensor
+
+# column chunks of the C4 all-gather / SpMM pipeline (1 = one blocking all-gather per SpMM)
+C4_CHUNKS = int(os.environ.get("SGF_C4_CHUNKS", "2"))
+C4_MIN_CHUNK_BYTES = 256      # gathered rows stay >= two full 128-byte lines per neighbour
 
 
 def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -72,6 +77,45 @@ class Comm:
         out = torch.empty((self.world * self.block, h), dtype=x_local.dtype, device=x_local.device)
         dist.all_gather_into_tensor(out, xl, group=self.group)
         return out[:self.n_global]
+
+    def c4_chunks(self, h: int, elem_size: int) -> int:
+        """Column chunks of the C4 pipeline (C4_CHUNKS, reduced until the chunk rows are >= C4_MIN_CHUNK_BYTES)."""
+        if not self.active or self.world == 1:
+            return 1
+        want = C4_CHUNKS
+        while want > 1 and (h % want != 0 or (h // want) * elem_size < C4_MIN_CHUNK_BYTES):
+            want -= 1
+        return want
+
+    def spmm_gathered(self, spmm, rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x_local: Tensor, heavy=None) -> Tensor:
+        """C4 + SpMM: y[rows of this rank] = scale * A[rows, :] @ all_gather(x_local).
+
+        The operand is exchanged in column chunks, each an asynchronous all-gather on NCCL's stream; the SpMM of chunk c
+        (`spmm(rowptr, col, row_scale, x_chunk, out=y[:, chunk], heavy=...)`, i.e. kernels.spmm) starts as soon as chunk c
+        has arrived and overlaps the transfer of chunk c+1.  On uniform random graphs every remote row is a halo row, so
+        the exchange cannot be smaller than the all-gather; it can only be hidden."""
+        if not self.active or self.world == 1:
+            return spmm(rowptr, col, row_scale, x_local, heavy=heavy)
+        n_loc, h = x_local.shape
+        nch = self.c4_chunks(h, x_local.element_size())
+        if nch == 1:
+            return spmm(rowptr, col, row_scale, self.allgather_rows(x_local), heavy=heavy)
+        hc = h // nch
+        dev, dt = x_local.device, x_local.dtype
+        pending = []
+        for c in range(nch):
+            xc = torch.zeros((self.block, hc), dtype=dt, device=dev) if n_loc != self.block else \
+                torch.empty((self.block, hc), dtype=dt, device=dev)
+            xc[:n_loc].copy_(x_local[:, c * hc:(c + 1) * hc])
+            gc = torch.empty((self.world * self.block, hc), dtype=dt, device=dev)
+            pending.append((dist.all_gather_into_tensor(gc, xc, group=self.group, async_op=True), gc, xc))
+        n_rows = rowptr.numel() - 1
+        # same pitch rule as kernels.alloc_act (rows 16-byte aligned); chunk offsets are multiples of 256 bytes
+        out = torch.empty((n_rows, h), dtype=dt, device=dev)
+        for c, (work, gc, _) in enumerate(pending):
+            work.wait()
+            spmm(rowptr, col, row_scale, gc[:self.n_global], out=out[:, c * hc:(c + 1) * hc], heavy=heavy)
+        return out
 
 
 SINGLE = Comm(None)

@@ -361,7 +361,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     out = x0
     for i in range(nl):
         last = i == nl - 1
-        y = K.spmm(graph.rowptr, graph.col, dinv, comm.allgather_rows(cur_s), heavy=graph.heavy)    # C4: operand rows of every shard
+        y = comm.spmm_gathered(K.spmm, graph.rowptr, graph.col, dinv, cur_s, heavy=graph.heavy)    # C4: operand rows of every shard
         st = _stat_bufs(use_bn, training, h, dev)      # BatchNorm sums come out of the GEMM epilogue
         if use_init:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
@@ -444,7 +444,7 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
         else:
             dys = K.axpby(dz, None, 1.0, 0.0, row_scale=dinv)
         # = A^T (dinv . dy): gradient w.r.t. the pre-scaled SpMM input (C4: gradient rows of every shard)
-        dy_scaled = K.spmm(rowptr_t, col_t, None, comm.allgather_rows(dys), heavy=graph.heavy_t)
+        dy_scaled = comm.spmm_gathered(K.spmm, rowptr_t, col_t, None, dys, heavy=graph.heavy_t)
         dy_plain = None
     # input layer epilogue: gradient of x0 = accumulated dx0 (+ dinv * dy_scaled from layer 0's SpMM)
     if nl == 0:
@@ -512,7 +512,7 @@ def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, tra
         hout = P[wname].shape[0]
         t = K.gemm_nt([cur_op], [_w(P, wname, prec)], [(0, 0, 0, 0, cur_k)], hout, K.alloc_act(n, hout, prec.act_dtype, dev),
                       row_scale=dinv)
-        s = K.spmm(graph.rowptr, graph.col, dinv, comm.allgather_rows(t), heavy=graph.heavy)
+        s = comm.spmm_gathered(K.spmm, graph.rowptr, graph.col, dinv, t, heavy=graph.heavy)
         zb = P.get(f"{pfx}convs.{i}.bias")
         if last:
             out, _ = K.bn_fwd(s, None, mix, None, None, None, None, zb, False, False, 0.0, 0, gw, None, True, False)
@@ -561,7 +561,7 @@ def gcn_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: Pre
         gs = 1.0
         if zb is not None:
             grads[f"{pfx}convs.{i}.bias"] = colsum
-        u = K.spmm(rowptr_t, col_t, dinv, comm.allgather_rows(dzs), heavy=graph.heavy_t)        # = Â^T dz = gradient of (x W^T)
+        u = comm.spmm_gathered(K.spmm, rowptr_t, col_t, dinv, dzs, heavy=graph.heavy_t)        # = Â^T dz = gradient of (x W^T)
         u_op = K.as_operand(u, prec.planes)
         wname = f"{pfx}convs.{i}.lin.weight"
         dw = torch.empty((hout, L["cur_k"]), dtype=torch.float32, device=dev)
@@ -586,7 +586,8 @@ def head_forward(P, cfg: dict, feats: List[Tensor], prec: Precision, tape: Optio
     w = _w(P, "fc.weight", prec)
     ops = [K.as_operand(f, prec.planes) for f in feats]
     pairs = [(j, 0, 0, j * h, h) for j in range(len(feats))]
-    out = torch.empty((n, c), dtype=torch.float32, device=feats[0].device)
+    # pitch padded to a 16-byte multiple (c = 47 -> 48 floats): the GEMM epilogue can then use its TMA-store path
+    out = K.alloc_act(n, c, torch.float32, feats[0].device)
     K.gemm_nt(ops, [w], pairs, c, out, bias=P["fc.bias"])
     if tape is not None:
         tape.update(ops=ops, nfeat=len(feats))

@@ -40,9 +40,11 @@ def _worker(rank, world, port, fixture, outdir):
     import kernel_emu
     from sgformer_b200 import engine as E
     from sgformer_b200 import functional as Fn
+    from sgformer_b200 import dist as D
     from sgformer_b200.dist import Comm
     E.K = kernel_emu
     Fn.K = kernel_emu
+    D.C4_CHUNKS, D.C4_MIN_CHUNK_BYTES = 2, 8     # exercise the column-chunked all-gather / SpMM pipeline on the tiny fixtures
     fx = torch.load(fixture, weights_only=False)
     cfg = _cfg_from_oracle(fx["cfg"])
     sd = fx["state_dict"]
