@@ -19,8 +19,10 @@ import torch.distributed as dist
 
 Tensor = torch.Tensor
 
-# column chunks of the C4 all-gather / SpMM pipeline (1 = one blocking all-gather per SpMM)
-C4_CHUNKS = int(os.environ.get("SGF_C4_CHUNKS", "2"))
+# Column chunks of the C4 all-gather / SpMM pipeline (1 = one blocking all-gather per SpMM).  Measured on 2 B200s at the
+# products shape (profiles/r1_scaling.md): 60.1 ms/step with 1 chunk, 61.2 with 2, 61.3 with 4 - NCCL's all-gather kernels need SMs
+# that the HBM-bound SpMM grid already fills, so the transfer is not hidden and the narrower SpMMs cost more; default stays 1.
+C4_CHUNKS = int(os.environ.get("SGF_C4_CHUNKS", "1"))
 C4_MIN_CHUNK_BYTES = 256      # gathered rows stay >= two full 128-byte lines per neighbour
 
 
