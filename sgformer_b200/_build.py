@@ -62,5 +62,29 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_variant(name, extra_flags, only=("spmm.cu",)):
+    """Tuning aid: libsgformer_b200_<name>.so with `extra_flags` (e.g. ["-DSGF_SPMM_UNROLL=8"]) applied to the sources in
+    `only`; all other objects are shared with the main build.  Load it with scripts/bench_*.py --lib."""
+    build()
+    vdir = os.path.join(OBJ_DIR, name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in _sources():
+        base = os.path.basename(src)
+        if base in only:
+            obj = os.path.join(vdir, base[:-3] + ".o")
+            r = subprocess.run([NVCC] + ARCH_FLAGS + CFLAGS + list(extra_flags) + ["-c", src, "-o", obj], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        else:
+            obj = os.path.join(OBJ_DIR, base[:-3] + ".o")
+        objs.append(obj)
+    out = os.path.join(LIB_DIR, f"libsgformer_b200_{name}.so")
+    r = subprocess.run([NVCC] + ARCH_FLAGS + ["-shared", "-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

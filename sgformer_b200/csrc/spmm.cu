@@ -21,51 +21,75 @@
 namespace sgf {
 
 constexpr int kSpmmBlock = 256;
-constexpr int kUnroll = 4;
+#ifndef SGF_SPMM_UNROLL
+#define SGF_SPMM_UNROLL 4
+#endif
+#ifndef SGF_SPMM_MIN_BLOCKS
+#define SGF_SPMM_MIN_BLOCKS 4
+#endif
+// Tuning knobs, measured on a B200 at the products shape (scripts/gpu_spmm_ab.sh, profiles/r1c_spmm_variants.txt): 4 rows in flight
+// x 4 CTAs/SM = 9.74 ms/launch; 8 rows x 3 CTAs/SM 9.72; software-pipelining the rowptr -> column-id -> feature-row chain
+// across a warp's rows (SGF_SPMM_PIPELINE=1) 10.0-10.8 ms.  The gather already saturates the memory system (1.03x the copy
+// bandwidth, 81 % of the DRAM peak in ncu); extra memory-level parallelism buys nothing, so the simple loop stays.
+#ifndef SGF_SPMM_PIPELINE
+#define SGF_SPMM_PIPELINE 0
+#endif
+constexpr int kUnroll = SGF_SPMM_UNROLL;
+constexpr int kMinBlocks = SGF_SPMM_MIN_BLOCKS;
 
-// gather-accumulate the neighbour rows col[s..e) of x into acc (fp32), all lane groups of the warp cooperating
+// gather-accumulate up to 32 neighbour rows whose ids sit one per lane in my_idx (cnt valid), all lane groups cooperating
+template <typename T, int CPL>
+__device__ __forceinline__ void gather_item(int my_idx, int cnt, const T* __restrict__ x, int64_t ldx, int groups, int grp,
+                                            const int (&coff)[CPL], const bool (&cval)[CPL], float (&acc)[CPL][Vec16<T>::N]) {
+    constexpr int VN = Vec16<T>::N;
+    for (int j0 = 0; j0 < cnt; j0 += groups * kUnroll) {
+        uint4 v[kUnroll][CPL];
+        int nb[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int j = j0 + u * groups + grp;
+            int t = __shfl_sync(0xffffffffu, my_idx, j & 31);
+            nb[u] = j < cnt ? t : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
+                else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float f[VN];
+                Vec16<T>::unpack(v[u][c], f);
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[c][i] += f[i];
+            }
+    }
+}
+
+// gather-accumulate the neighbour rows col[s..e) of x into acc (fp32)
 template <typename T, int CPL>
 __device__ __forceinline__ void gather_range(const int32_t* __restrict__ col, const T* __restrict__ x, int64_t ldx, int64_t s, int64_t e,
                                              int lane, int groups, int grp, const int (&coff)[CPL], const bool (&cval)[CPL],
                                              float (&acc)[CPL][Vec16<T>::N]) {
-    constexpr int VN = Vec16<T>::N;
     for (int64_t base = s; base < e; base += 32) {
         const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
         const int my_idx = lane < cnt ? ldg_nc_na_s32(col + base + lane) : -1;
-        for (int j0 = 0; j0 < cnt; j0 += groups * kUnroll) {
-            uint4 v[kUnroll][CPL];
-            int nb[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                int j = j0 + u * groups + grp;
-                int t = __shfl_sync(0xffffffffu, my_idx, j & 31);
-                nb[u] = j < cnt ? t : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
-                    else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    float f[VN];
-                    Vec16<T>::unpack(v[u][c], f);
-#pragma unroll
-                    for (int i = 0; i < VN; ++i) acc[c][i] += f[i];
-                }
-        }
+        gather_item<T, CPL>(my_idx, cnt, x, ldx, groups, grp, coff, cval, acc);
     }
 }
 
-// one warp per output row; rows longer than max_len (> 0) are left to the segmented path below
+// One warp per output row, rows r = warp, warp + nwarps, ...; rows longer than max_len (> 0) are left to the segmented path
+// below.  SGF_SPMM_PIPELINE=1 software-pipelines the dependent chain rowptr -> column ids -> feature rows across the warp's work
+// items (an item = up to 32 neighbours of one row): while the gathers of item i are in flight, the column ids of item i+1 (same
+// row or the warp's next row) and the rowptr entries of the row after next are already loading (slower on B200, see above).
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kSpmmBlock, 4)
+__global__ void __launch_bounds__(kSpmmBlock, kMinBlocks)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
                  const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2,
                  int64_t max_len) {
@@ -85,6 +109,73 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
         cval[c] = ch < chunks;
         coff[c] = ch * VN;
     }
+#if SGF_SPMM_PIPELINE
+    int64_t r = warp0;
+    if (r >= n_rows) return;
+    // current row [s, e) (a skipped hub row behaves like an empty row that is not stored), next row [sn, en)
+    int64_t s = rowptr[r], e = rowptr[r + 1];
+    bool skip = max_len > 0 && e - s > max_len;
+    if (skip) e = s;
+    int64_t rn = r + nwarps, sn = 0, en = 0;
+    if (rn < n_rows) { sn = rowptr[rn]; en = rowptr[rn + 1]; }
+    int64_t base = s;
+    int idx = (base + lane < e) ? ldg_nc_na_s32(col + base + lane) : -1;
+    float acc[CPL][VN];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
+    while (true) {
+        const int cnt = (int)((e - base) < 32 ? (e - base) : 32);      // 0 for an empty row
+        const bool last = base + 32 >= e;                               // last item of this row
+        // ---- put the next item's column ids (and, at a row end, the rowptr pair of the row after next) in flight ----
+        int64_t nbase, ne;
+        bool nskip = false;
+        int64_t rnn = rn, snn = 0, enn = 0;
+        if (!last) { nbase = base + 32; ne = e; }
+        else {
+            nskip = max_len > 0 && en - sn > max_len;
+            nbase = sn; ne = nskip ? sn : en;
+            rnn = rn + nwarps;
+            if (rnn < n_rows) { snn = rowptr[rnn]; enn = rowptr[rnn + 1]; }
+        }
+        const bool have_next = !last || rn < n_rows;
+        const int nidx = (have_next && nbase + lane < ne) ? ldg_nc_na_s32(col + nbase + lane) : -1;
+        // ---- this item ----
+        gather_item<T, CPL>(idx, cnt, x, ldx, groups, grp, coff, cval, acc);
+        if (last) {
+            if (!skip) {
+                for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+                        for (int i = 0; i < VN; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], o);
+                }
+                const float rs = row_scale ? row_scale[r] : 1.0f;
+                if (grp == 0) {
+                    T* dst = y + r * ldy;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        if (!cval[c]) continue;
+                        float f[VN];
+#pragma unroll
+                        for (int i = 0; i < VN; ++i) f[i] = acc[c][i] * rs;
+                        stg_na(dst + coff[c], Vec16<T>::pack(f));
+                    }
+                }
+            }
+            if (rn >= n_rows) break;
+            r = rn; s = sn; e = ne; skip = nskip;
+            rn = rnn; sn = snn; en = enn;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
+        }
+        base = nbase;
+        idx = nidx;
+    }
+#else
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
         const int64_t s = rowptr[r];
         const int64_t e = rowptr[r + 1];
@@ -114,12 +205,13 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
             }
         }
     }
+#endif
 }
 
 // hub rows (power-law graphs): a row longer than the threshold is cut into segments, one warp per segment writes an fp32
 // partial sum, and a second kernel adds a row's partials in fixed order (deterministic), scales and stores the row.
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kSpmmBlock, 4)
+__global__ void __launch_bounds__(kSpmmBlock, kMinBlocks)
 spmm_segments_kernel(const int32_t* __restrict__ col, const T* __restrict__ x, int64_t ldx, const int64_t* __restrict__ seg_start,
                      const int32_t* __restrict__ seg_len, int64_t n_seg, float* __restrict__ partial, int h, int chunks,
                      int lpr_log2) {
@@ -193,7 +285,7 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* r
     if (n_rows == 0) return SGF_OK;
     int64_t warps_needed = n_rows;
     int64_t blocks = (warps_needed * 32 + kSpmmBlock - 1) / kSpmmBlock;
-    int64_t cap = (int64_t)num_sms() * 4 * 8;  // 8 waves of 4 resident CTAs per SM, grid-stride beyond
+    int64_t cap = (int64_t)num_sms() * kMinBlocks * 8;  // 8 waves of the resident CTAs per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
     const T* xp = static_cast<const T*>(x);
     T* yp = static_cast<T*>(y);
@@ -227,7 +319,7 @@ static int launch_heavy(const int32_t* col, const float* row_scale, const void* 
     const int lpr = 1 << lpr_log2;
     const int cpl = (chunks + lpr - 1) / lpr;
     int64_t blocks = (n_seg * 32 + kSpmmBlock - 1) / kSpmmBlock;
-    int64_t cap = (int64_t)num_sms() * 4 * 8;
+    int64_t cap = (int64_t)num_sms() * kMinBlocks * 8;
     if (blocks > cap) blocks = cap;
     const T* xp = static_cast<const T*>(x);
 #define SGF_SEG_CASE(N)                                                                                                 \
