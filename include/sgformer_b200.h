@@ -72,6 +72,22 @@ int sgf_subgraph(const int64_t* edge_index, int64_t nnz, int64_t n, const int64_
                  int32_t* node_map, int64_t* out_edge_index /* [2,nnz] capacity, pitch nnz */,
                  int64_t* out_count, void* ws, size_t ws_bytes, void* stream);
 int sgf_subgraph_ws_bytes(int64_t nnz, int64_t n, size_t* bytes);
+
+/* K10 — graph preprocessing on the device, bit-exact with torch_geometric 1.7.2 as the reference calls it:
+ *   to_undirected(edge_index)                 large/main.py:76, medium/main.py:94   = coalesce([ei | ei.flip(0)]): every edge
+ *                                             in both directions, sorted by (row, col), duplicates removed;
+ *   remove_self_loops(edge_index)             large/main.py:78, large/main-batch.py:97: drops row == col, keeps the order;
+ *   add_self_loops(edge_index, num_nodes=n)   large/main.py:79, large/main-batch.py:98: appends (i, i), i = 0..n-1.
+ * edge_index: int64 [2, nnz] row-major (row r at edge_index + r*nnz).  Outputs are int64 [2, capacity] with the pitch stated
+ * per function; out_count is a device int64 scalar (valid prefix length of each output row). */
+int sgf_to_undirected_ws_bytes(int64_t nnz, int64_t n, size_t* bytes);
+int sgf_to_undirected(const int64_t* edge_index, int64_t nnz, int64_t n, int64_t* out_edge_index /* pitch 2*nnz */,
+                      int64_t* out_count, void* ws, size_t ws_bytes, void* stream);
+int sgf_remove_self_loops_ws_bytes(int64_t nnz, size_t* bytes);
+int sgf_remove_self_loops(const int64_t* edge_index, int64_t nnz, int64_t* out_edge_index /* pitch nnz */, int64_t* out_count,
+                          void* ws, size_t ws_bytes, void* stream);
+int sgf_add_self_loops(const int64_t* edge_index, int64_t nnz, int64_t n, int64_t* out_edge_index /* [2, nnz+n], pitch nnz+n */,
+                       void* stream);
 /* K9 on the CSR: the induced subgraph of `subset` emitted directly as the subset's own CSR (rows = subset order, columns
  * = positions in subset, sorted; dinv from the induced in-degrees) — the structure GraphConv needs for a mini-batch, in
  * O(sum of the subset rows' lengths) instead of PyG subgraph's O(E) mask per batch + a CSR rebuild.
@@ -241,6 +257,13 @@ int sgf_head_mean(const void* x, int64_t ldx, int64_t rows, int heads, int d, in
  * mask: uint8 [rows] or NULL (all rows). */
 int sgf_softmax_nll(const float* logits, int64_t ld, const int64_t* labels, const uint8_t* mask, int64_t rows, int c,
                     float scale, float* loss, float* dlogits, int64_t ld_d, void* stream);
+
+/* K11 - evaluation on the device: number of rows r = idx[i], i < m (all rows when idx is NULL, then m = rows)
+ * with argmax_j logits[r, j] == labels[r] (first maximum on ties), and optionally the sum of -log_softmax(logits[r])[labels[r]].
+ * Replaces eval_acc (large/data_utils.py:210-220: argmax, D2H, numpy loop per split) and the valid_loss of evaluate()
+ * (large/eval.py:28-31) for single-column int64 labels.  correct: device int64, nll_sum: device fp64 or NULL. */
+int sgf_eval_acc(const float* logits, int64_t ld, const int64_t* labels, const int64_t* idx, int64_t m, int64_t rows, int32_t c,
+                 int64_t* correct, double* nll_sum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Linear attention glue (full_attention_conv, medium/ours.py:14-34; backward per SURVEY.md Appendix A.1)

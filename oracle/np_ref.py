@@ -70,3 +70,39 @@ def spmm_fp64(edge_index, n, x):
         dinv = np.where(deg > 0, 1.0 / np.sqrt(deg), 0.0)
     a = sp.coo_matrix((dinv[dst] * dinv[src], (dst, src)), shape=(n, n)).tocsr()
     return a @ np.asarray(x, dtype=np.float64)
+
+
+# ---- graph preprocessing around the model (torch_geometric 1.7.2 semantics; integer, bit-exact) -------------------------------
+def to_undirected(edge_index, n):
+    """`torch_geometric.utils.to_undirected` as called at large/main.py:76 and medium/main.py:94: concatenate every edge
+    with its reverse, then `torch_sparse.coalesce` = sort by row*n+col and drop duplicates.  int64 [2, nnz']."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    row = np.concatenate([ei[0], ei[1]])
+    col = np.concatenate([ei[1], ei[0]])
+    key = np.unique(row * np.int64(n) + col)          # sorted, deduplicated
+    return np.stack([key // n, key % n]) if key.size else np.zeros((2, 0), dtype=np.int64)
+
+
+def remove_self_loops(edge_index):
+    """`remove_self_loops` (large/main.py:78, large/main-batch.py:97): mask = row != col, order preserved."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    return ei[:, ei[0] != ei[1]]
+
+
+def add_self_loops(edge_index, n):
+    """`add_self_loops(edge_index, num_nodes=n)` (large/main.py:79, large/main-batch.py:98): append (i, i) for i in 0..n-1."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    loops = np.arange(n, dtype=np.int64)
+    return np.concatenate([ei, np.stack([loops, loops])], axis=1)
+
+
+def eval_acc(y_true, y_pred_logits):
+    """`eval_acc` of the reference (large/data_utils.py:210-220) for integer labels [m, k]: per label column, the fraction of
+    rows whose argmax over the logits equals the label (every integer label counts as labelled); mean over columns."""
+    y_true = np.asarray(y_true)
+    y_pred = np.asarray(y_pred_logits).argmax(axis=-1)[:, None]
+    accs = []
+    for i in range(y_true.shape[1]):
+        correct = y_true[:, i] == y_pred[:, i]
+        accs.append(float(np.sum(correct)) / len(correct))
+    return sum(accs) / len(accs)

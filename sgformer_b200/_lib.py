@@ -57,6 +57,11 @@ _SIGS = {
     "sgf_csr_build": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_csr_build_rect": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_subgraph_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
+    "sgf_to_undirected_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
+    "sgf_to_undirected": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "sgf_remove_self_loops_ws_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
+    "sgf_remove_self_loops": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "sgf_add_self_loops": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sgf_subgraph": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_spmm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _i64, _vp]),
     "sgf_spmm_heavy": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
@@ -80,6 +85,7 @@ _SIGS = {
     "sgf_pack_operand": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, _vp, _i64, C.c_int, _i64, _vp, _vp, _vp]),
     "sgf_csr_subset_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "sgf_csr_subset": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "sgf_eval_acc": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp]),
     "sgf_softmax_nll": (C.c_int, [_vp, _i64, _vp, _vp, _i64, C.c_int, _f32, _vp, _vp, _i64, _vp]),
     "sgf_head_mean": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp]),
     "sgf_attn_prepare_fwd": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp, _i64,

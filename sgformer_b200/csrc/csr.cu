@@ -368,6 +368,69 @@ __global__ void subset_fill_kernel(const int64_t* __restrict__ rowptr, const int
     }
 }
 
+// ---- K10: graph preprocessing (torch_geometric.utils.to_undirected / remove_self_loops / add_self_loops) -----------------------
+// remove_self_loops: order-preserving filter (flags -> scan -> scatter)
+__global__ void selfloop_flag_kernel(const int64_t* __restrict__ ei, int64_t nnz, int* __restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) flags[e] = ei[e] != ei[nnz + e];
+}
+__global__ void compact_edges_kernel(const int64_t* __restrict__ ei, int64_t nnz, const int* __restrict__ flags,
+                                     const int64_t* __restrict__ pos, int64_t* __restrict__ out, int64_t out_pitch) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        if (!flags[e]) continue;
+        int64_t p = pos[e];
+        out[p] = ei[e];
+        out[out_pitch + p] = ei[nnz + e];
+    }
+}
+// add_self_loops: [edge_index | (i, i) for i in 0..n)
+__global__ void add_self_loops_kernel(const int64_t* __restrict__ ei, int64_t nnz, int64_t n, int64_t* __restrict__ out) {
+    const int64_t pitch = nnz + n;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < pitch; e += stride) {
+        out[e] = e < nnz ? ei[e] : e - nnz;
+        out[pitch + e] = e < nnz ? ei[nnz + e] : e - nnz;
+    }
+}
+// to_undirected = coalesce([ei | ei.flip(0)]): the doubled list is never materialised - the CSR count / fill kernels run once per
+// direction into the same rows, rows are sorted, then a sorted row's first occurrences are counted and emitted as COO (row, col).
+__global__ void __launch_bounds__(256) row_unique_count_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                               int64_t n, int* __restrict__ ucount) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        int cnt = 0;
+        for (int64_t j = s + lane; j < e; j += 32) cnt += (j == s || col[j] != col[j - 1]) ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) ucount[r] = cnt;
+    }
+}
+__global__ void __launch_bounds__(256) row_unique_emit_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                              int64_t n, const int64_t* __restrict__ uptr,
+                                                              int64_t* __restrict__ out, int64_t out_pitch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        int64_t base = uptr[r];
+        for (int64_t j0 = s; j0 < e; j0 += 32) {
+            const int64_t j = j0 + lane;
+            const bool keep = j < e && (j == s || col[j] != col[j - 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int64_t p = base + __popc(m & ((1u << lane) - 1u));
+                out[p] = r;
+                out[out_pitch + p] = col[j];
+            }
+            base += __popc(m);
+        }
+    }
+}
+
 static inline int grid_for(int64_t work, int block, int per_sm = 8) {
     int64_t g = (work + block - 1) / block;
     int64_t cap = (int64_t)num_sms() * per_sm;
@@ -433,6 +496,22 @@ static CsrWs carve_ws(void* ws, int64_t nnz, int64_t n) {
     return w;
 }
 
+// per-row ascending sort of col (tiers by row length; see the kernels)
+static int sort_rows(const int64_t* rowptr, int32_t* col, int64_t n, const CsrWs& w, cudaStream_t st) {
+    csr_sort_rows_warp_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(rowptr, n, col, w.long_rows, w.n_long);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int64_t share = w.scratch_elems / kHubBlocks;
+    // queued rows: (256, 2048] in shared memory across the whole chip; (2048, share] in global scratch by kHubBlocks
+    // blocks; (share, scratch] by a single block.
+    csr_sort_rows_block_kernel<<<num_sms() * 4, 256, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, 0, 0, kSortSmemMax);
+    SGF_LAUNCH_CHECK(); count_launch();
+    csr_sort_rows_block_kernel<<<kHubBlocks, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, share, kSortSmemMax, share);
+    SGF_LAUNCH_CHECK(); count_launch();
+    csr_sort_rows_block_kernel<<<1, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, w.scratch_elems, share, w.scratch_elems);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
 extern "C" int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
     if (!bytes || nnz < 0 || n < 0) return SGF_ERR_ARG;
     *bytes = carve_ws(nullptr, nnz, n).bytes;
@@ -470,17 +549,8 @@ extern "C" int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_
         SGF_LAUNCH_CHECK(); count_launch();
     }
     if (n > 0) {
-        csr_sort_rows_warp_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(rowptr, n, col, w.long_rows, w.n_long);
-        SGF_LAUNCH_CHECK(); count_launch();
-        int64_t share = w.scratch_elems / kHubBlocks;
-        // queued rows: (256, 2048] in shared memory across the whole chip; (2048, share] in global scratch by kHubBlocks
-        // blocks; (share, scratch] by a single block.
-        csr_sort_rows_block_kernel<<<num_sms() * 4, 256, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, 0, 0, kSortSmemMax);
-        SGF_LAUNCH_CHECK(); count_launch();
-        csr_sort_rows_block_kernel<<<kHubBlocks, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, share, kSortSmemMax, share);
-        SGF_LAUNCH_CHECK(); count_launch();
-        csr_sort_rows_block_kernel<<<1, 1024, 0, st>>>(rowptr, col, w.long_rows, w.n_long, w.scratch, w.scratch_elems, share, w.scratch_elems);
-        SGF_LAUNCH_CHECK(); count_launch();
+        int rcs = sort_rows(rowptr, col, n, w, st);
+        if (rcs) return rcs;
         if (dinv) {
             csr_dinv_kernel<<<grid_for(n, 256), 256, 0, st>>>(rowptr, n, dinv);
             SGF_LAUNCH_CHECK(); count_launch();
@@ -583,5 +653,112 @@ extern "C" int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t
         csr_dinv_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(out_rowptr, n_sub, dinv);
         SGF_LAUNCH_CHECK(); count_launch();
     }
+    return SGF_OK;
+}
+
+// ---- K10 host side ---------------------------------------------------------------------------------------------------------
+// workspace of remove_self_loops: flags int32[nnz+1] | pos int64[nnz+1] | block_sums
+extern "C" int sgf_remove_self_loops_ws_bytes(int64_t nnz, size_t* bytes) {
+    if (!bytes || nnz < 0) return SGF_ERR_ARG;
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nb = (nnz + per_block - 1) / per_block + 1;
+    *bytes = align_up((size_t)(nnz + 1) * 4, 256) * 2 + align_up((size_t)(nnz + 1) * 8, 256) + align_up((size_t)nb * 8, 256) + 256;
+    return SGF_OK;
+}
+
+extern "C" int sgf_remove_self_loops(const int64_t* edge_index, int64_t nnz, int64_t* out_edge_index, int64_t* out_count, void* ws,
+                                     size_t ws_bytes, void* stream) {
+    if (nnz < 0 || !out_count || !ws || (nnz > 0 && (!edge_index || !out_edge_index))) return SGF_ERR_ARG;
+    size_t need = 0;
+    sgf_remove_self_loops_ws_bytes(nnz, &need);
+    if (ws_bytes < need) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nnz == 0) {
+        SGF_CUDA_TRY(cudaMemsetAsync(out_count, 0, 8, st));
+        return SGF_OK;
+    }
+    char* base = (char*)ws;
+    size_t off = 0;
+    int* flags = (int*)(base + off); off += align_up((size_t)(nnz + 1) * 4, 256);
+    int* cursor = (int*)(base + off); off += align_up((size_t)(nnz + 1) * 4, 256);
+    int64_t* pos = (int64_t*)(base + off); off += align_up((size_t)(nnz + 1) * 8, 256);
+    int64_t* block_sums = (int64_t*)(base + off);
+    selfloop_flag_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, nnz, flags);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int rc = launch_scan(flags, nnz, 0, pos, block_sums, out_count, cursor, st);
+    if (rc) return rc;
+    compact_edges_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, nnz, flags, pos, out_edge_index, nnz);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_add_self_loops(const int64_t* edge_index, int64_t nnz, int64_t n, int64_t* out_edge_index, void* stream) {
+    if (nnz < 0 || n < 0 || (nnz > 0 && !edge_index) || (nnz + n > 0 && !out_edge_index)) return SGF_ERR_ARG;
+    if (nnz + n == 0) return SGF_OK;
+    add_self_loops_kernel<<<grid_for(nnz + n, 256), 256, 0, (cudaStream_t)stream>>>(edge_index, nnz, n, out_edge_index);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+// workspace of to_undirected: CsrWs(2 nnz, n) | rowptr int64[n+1] | uptr int64[n+1] | ucount int32[n+1] | ucursor int32[n+1] |
+//                             block_sums2 | col int32[2 nnz]
+struct UndWs {
+    CsrWs csr; int64_t* rowptr; int64_t* uptr; int* ucount; int* ucursor; int64_t* block_sums2; int32_t* col; size_t bytes;
+};
+static UndWs carve_und(void* ws, int64_t nnz, int64_t n) {
+    UndWs u;
+    u.csr = carve_ws(ws, 2 * nnz, n);
+    size_t off = align_up(u.csr.bytes, 256);
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    char* base = (char*)ws;
+    int64_t per_block = (int64_t)kScanBlock * kScanItems;
+    int64_t nb = (n + per_block - 1) / per_block + 1;
+    size_t o_rp = take((size_t)(n + 1) * 8), o_up = take((size_t)(n + 1) * 8), o_uc = take((size_t)(n + 1) * 4);
+    size_t o_cu = take((size_t)(n + 1) * 4), o_bs = take((size_t)nb * 8), o_col = take((size_t)(2 * nnz + 1) * 4);
+    u.rowptr = (int64_t*)(base + o_rp); u.uptr = (int64_t*)(base + o_up); u.ucount = (int*)(base + o_uc);
+    u.ucursor = (int*)(base + o_cu); u.block_sums2 = (int64_t*)(base + o_bs); u.col = (int32_t*)(base + o_col);
+    u.bytes = off;
+    return u;
+}
+
+extern "C" int sgf_to_undirected_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
+    if (!bytes || nnz < 0 || n < 0) return SGF_ERR_ARG;
+    *bytes = carve_und(nullptr, nnz, n).bytes;
+    return SGF_OK;
+}
+
+extern "C" int sgf_to_undirected(const int64_t* edge_index, int64_t nnz, int64_t n, int64_t* out_edge_index, int64_t* out_count,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (nnz < 0 || n < 0 || n >= (int64_t)INT32_MAX || !out_count || !ws || (nnz > 0 && (!edge_index || !out_edge_index)))
+        return SGF_ERR_ARG;
+    UndWs u = carve_und(ws, nnz, n);
+    if (ws_bytes < u.bytes) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nnz == 0 || n == 0) {
+        SGF_CUDA_TRY(cudaMemsetAsync(out_count, 0, 8, st));
+        return nnz == 0 ? SGF_OK : SGF_ERR_ARG;
+    }
+    const CsrWs& w = u.csr;
+    const int64_t* row = edge_index;
+    const int64_t* colv = edge_index + nnz;
+    SGF_CUDA_TRY(cudaMemsetAsync(w.counts, 0, (size_t)(n + 1) * 4, st));
+    SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
+    // both directions into the same rows: (row -> col) and (col -> row)
+    csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(row, colv, nnz, 0, n, n, 0, w.counts, w.err);
+    SGF_LAUNCH_CHECK(); count_launch();
+    csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(colv, row, nnz, 0, n, n, 0, w.counts, w.err);
+    SGF_LAUNCH_CHECK(); count_launch();
+    int rc = launch_scan(w.counts, n, 0, u.rowptr, w.block_sums, w.total, w.cursor, st);
+    if (rc) return rc;
+    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(row, colv, nnz, 0, n, n, 0, u.rowptr, w.cursor, u.col);
+    SGF_LAUNCH_CHECK(); count_launch();
+    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(colv, row, nnz, 0, n, n, 0, u.rowptr, w.cursor, u.col);
+    SGF_LAUNCH_CHECK(); count_launch();
+    if ((rc = sort_rows(u.rowptr, u.col, n, w, st))) return rc;
+    row_unique_count_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(u.rowptr, u.col, n, u.ucount);
+    SGF_LAUNCH_CHECK(); count_launch();
+    if ((rc = launch_scan(u.ucount, n, 0, u.uptr, u.block_sums2, out_count, u.ucursor, st))) return rc;
+    row_unique_emit_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(u.rowptr, u.col, n, u.uptr, out_edge_index, 2 * nnz);
+    SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

@@ -795,6 +795,47 @@ __global__ void __launch_bounds__(kRowBlock) softmax_nll_kernel(const float* __r
     if (lane == 0 && acc != 0.f) atomicAdd(loss, acc * scale);
 }
 
+// K11 - evaluation on the device: accuracy (argmax == label) and summed NLL of log_softmax over the rows idx[0..m) (all rows if
+// idx is NULL).  Replaces eval_acc (reference large/data_utils.py:210-220: argmax -> D2H -> numpy loop) and the valid_loss of
+// evaluate() (large/eval.py:28-31) for single-column integer labels.  Ties: first maximum, as numpy/torch argmax.
+__global__ void __launch_bounds__(kRowBlock) eval_acc_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ y,
+                                                              const int64_t* __restrict__ idx, int64_t m, int64_t rows, int c,
+                                                              unsigned long long* __restrict__ correct, double* __restrict__ nll_sum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long hit = 0;
+    double acc = 0.0;
+    for (int64_t i = warp; i < m; i += nwarps) {
+        const int64_t r = idx ? idx[i] : i;
+        if (r < 0 || r >= rows) continue;
+        const float* xr = x + r * ldx;
+        float best = -INFINITY;
+        int arg = c;
+        for (int j = lane; j < c; j += 32) {
+            const float v = xr[j];
+            if (v > best) { best = v; arg = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        const int64_t lab = y[r];
+        if (lane == 0 && lab == arg) ++hit;
+        if (nll_sum) {
+            float se = 0.f;
+            for (int j = lane; j < c; j += 32) se += expf(xr[j] - best);
+            se = warp_sum(se);
+            if (lane == 0 && lab >= 0 && lab < c) acc += (double)(best + logf(se) - xr[lab]);
+        }
+    }
+    if (lane == 0) {
+        if (hit) atomicAdd(correct, hit);
+        if (nll_sum && acc != 0.0) atomicAdd(nll_sum, acc);
+    }
+}
+
 }  // namespace sgf
 
 using namespace sgf;
@@ -1059,6 +1100,22 @@ extern "C" int sgf_softmax_nll(const float* logits, int64_t ld, const int64_t* l
     if (blocks > cap) blocks = cap;
     softmax_nll_kernel<<<(unsigned)blocks, kRowBlock, 0, (cudaStream_t)stream>>>(logits, ld, labels, mask, rows, c, scale, loss,
                                                                                dlogits, ld_d);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_eval_acc(const float* logits, int64_t ld, const int64_t* labels, const int64_t* idx, int64_t m, int64_t rows,
+                            int c, int64_t* correct, double* nll_sum, void* stream) {
+    if (m < 0 || rows < 0 || c <= 0 || !correct || (m > 0 && (!logits || !labels)) || ld < c) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_CUDA_TRY(cudaMemsetAsync(correct, 0, 8, st));
+    if (nll_sum) SGF_CUDA_TRY(cudaMemsetAsync(nll_sum, 0, 8, st));
+    if (m == 0) return SGF_OK;
+    int64_t blocks = (m * 32 + kRowBlock - 1) / kRowBlock;
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    eval_acc_kernel<<<(unsigned)blocks, kRowBlock, 0, st>>>(logits, ld, labels, idx, m, rows, c,
+                                                            reinterpret_cast<unsigned long long*>(correct), nll_sum);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

@@ -135,6 +135,48 @@ def subgraph(edge_index: Tensor, n: int, subset: Tensor) -> Tensor:
     return out[:, :k]
 
 
+def _edge_index(edge_index: Tensor) -> Tensor:
+    _use(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise TypeError("edge_index must be int64 [2, nnz]")
+    return edge_index.contiguous()
+
+
+def to_undirected(edge_index: Tensor, n: int) -> Tensor:
+    """K10: PyG to_undirected = every edge in both directions, sorted by (row, col), duplicates removed (bit-exact)."""
+    ei = _edge_index(edge_index)
+    nnz, dev = ei.shape[1], ei.device
+    out = torch.empty((2, max(2 * nnz, 1)), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_to_undirected_ws_bytes(nnz, n, C.byref(nbytes)), "sgf_to_undirected_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    check(lib().sgf_to_undirected(_p(ei), nnz, n, _p(out), _p(count), _p(ws), nbytes.value, _stream()), "sgf_to_undirected")
+    return out[:, :int(count.item())]
+
+
+def remove_self_loops(edge_index: Tensor) -> Tensor:
+    """K10: PyG remove_self_loops (order-preserving)."""
+    ei = _edge_index(edge_index)
+    nnz, dev = ei.shape[1], ei.device
+    out = torch.empty((2, max(nnz, 1)), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    nbytes = C.c_size_t(0)
+    check(lib().sgf_remove_self_loops_ws_bytes(nnz, C.byref(nbytes)), "sgf_remove_self_loops_ws_bytes")
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    check(lib().sgf_remove_self_loops(_p(ei), nnz, _p(out), _p(count), _p(ws), nbytes.value, _stream()), "sgf_remove_self_loops")
+    return out[:, :int(count.item())]
+
+
+def add_self_loops(edge_index: Tensor, n: int) -> Tensor:
+    """K10: PyG add_self_loops(edge_index, num_nodes=n): [edge_index | (i, i) for i < n]."""
+    ei = _edge_index(edge_index)
+    nnz = ei.shape[1]
+    out = torch.empty((2, nnz + n), dtype=torch.int64, device=ei.device)
+    check(lib().sgf_add_self_loops(_p(ei), nnz, n, _p(out), _stream()), "sgf_add_self_loops")
+    return out
+
+
 # bench.py sets this to a list to collect (start, end) CUDA events around every SpMM launch (roofline measurement)
 spmm_events = None
 
@@ -613,6 +655,26 @@ def softmax_nll(logits: Tensor, labels: Tensor, mask: Optional[Tensor], scale: f
     check(lib().sgf_softmax_nll(_p(logits), ld, _p(labels), _p(m), rows, c, scale, _p(loss), _p(d), c, _stream()),
           "sgf_softmax_nll")
     return loss, d
+
+
+def eval_acc(logits: Tensor, labels: Tensor, idx: Optional[Tensor] = None, want_loss: bool = False):
+    """K11: (accuracy, mean NLL of log_softmax | None) over the rows `idx` (all rows if None), computed on the device.
+    labels: int64 [rows] or [rows, 1] for ALL rows of `logits` (indexed by idx inside the kernel)."""
+    _use(logits)
+    if logits.dtype != torch.float32:
+        raise TypeError("eval_acc expects fp32 logits")
+    rows, c, ld = _mat(logits, "logits")
+    labels = labels.reshape(-1).contiguous()
+    if labels.dtype != torch.int64 or labels.numel() != rows:
+        raise ValueError("eval_acc: labels must be int64 with one entry per logits row")
+    if idx is not None:
+        idx = idx.reshape(-1).to(device=logits.device, dtype=torch.int64).contiguous()
+    m = rows if idx is None else idx.numel()
+    correct = torch.empty(1, dtype=torch.int64, device=logits.device)
+    nll = torch.empty(1, dtype=torch.float64, device=logits.device) if want_loss else None
+    check(lib().sgf_eval_acc(_p(logits), ld, _p(labels), _p(idx), m, rows, c, _p(correct), _p(nll), _stream()), "sgf_eval_acc")
+    acc = float(correct.item()) / m if m else float("nan")
+    return acc, (float(nll.item()) / m if want_loss and m else None)
 
 
 def launch_count() -> int:

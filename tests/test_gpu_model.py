@@ -333,3 +333,37 @@ def test_host_feeder_double_buffering():
         assert sb.item() == sum(range(i, i + 1000))
     with pytest.raises(RuntimeError):
         feeder.get()
+
+
+def test_evaluate_on_device_matches_reference_formula():
+    """sgformer_b200.eval.evaluate (K11) returns the tuple of large/eval.py:6-33: three accuracies, valid NLL, log_softmax(out)."""
+    from types import SimpleNamespace
+
+    from oracle import np_ref
+    from sgformer_b200.eval import evaluate
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    n, c = 3000, 11
+    logits = torch.randn(n, c, generator=g)
+    label = torch.randint(0, c, (n, 1), generator=g)
+    perm = torch.randperm(n, generator=g)
+    split = {"train": perm[:1500], "valid": perm[1500:2200], "test": perm[2200:]}
+
+    class Fixed(torch.nn.Module):
+        def forward(self, x, ei):
+            return logits.to(dev)
+
+    def eval_acc(y_true, y_pred):           # only the name is consulted on the device path
+        raise AssertionError("host metric must not be called")
+
+    ds = SimpleNamespace(graph={"node_feat": torch.zeros(n, 1, device=dev), "edge_index": torch.zeros(2, 0, dtype=torch.long, device=dev)},
+                         label=label.to(dev))
+    tr, va, te, vloss, out = evaluate(Fixed(), ds, {k: v.to(dev) for k, v in split.items()}, eval_acc, torch.nn.NLLLoss(),
+                                      SimpleNamespace(dataset="ogbn-products"))
+    for got, key in ((tr, "train"), (va, "valid"), (te, "test")):
+        assert got == np_ref.eval_acc(label[split[key]].numpy(), logits[split[key]].numpy())
+    lsm = torch.log_softmax(logits, 1)
+    ref_loss = torch.nn.functional.nll_loss(lsm[split["valid"]], label.squeeze(1)[split["valid"]]).item()
+    assert abs(vloss.item() - ref_loss) < 1e-5
+    assert torch.allclose(out.cpu(), lsm, atol=1e-6)
