@@ -171,6 +171,7 @@ int sgf_gemm_nt(const sgf_gemm_nt_args* args /* host */, void* stream);
  * A: bf16 [rows, m] row-major, B: bf16 [rows, n] row-major; m <= 256, n <= 256.
  * Used for K^T V (medium/ours.py:21), q^T gnum (its backward) and every weight gradient dW = dY^T X.
  * Deterministic two-stage reduction through `ws` (sgf_gemm_tn_ws_bytes).  transpose_out writes out[N,M]. */
+#define SGF_TN_MAX_PAIRS 6
 typedef struct {
     const void* a; int64_t lda; int32_t m;
     const void* b; int64_t ldb; int32_t n;
@@ -178,6 +179,10 @@ typedef struct {
     float* out; int64_t ldo; int32_t transpose_out;
     float alpha, beta; const float* alpha_dev;
     void* ws; size_t ws_bytes;
+    int32_t n_pairs;                            /* 0: one product of the columns [0,m) x [0,n).  > 0 (bf16x3 operands): the
+                                                   products A[:, a_off[i] : +m]^T B[:, b_off[i] : +n], i < n_pairs, are summed in
+                                                   the accumulator (offsets in elements, multiples of 64; lda/ldb cover them) */
+    int32_t a_off[SGF_TN_MAX_PAIRS], b_off[SGF_TN_MAX_PAIRS];
 } sgf_gemm_tn_args;
 int sgf_gemm_tn_ws_bytes(int32_t m, int32_t n, int64_t rows, size_t* bytes);
 int sgf_gemm_tn(const sgf_gemm_tn_args* args /* host */, void* stream);

@@ -46,6 +46,7 @@ class GemmTnArgs(C.Structure):
         ("out", _vp), ("ldo", _i64), ("transpose_out", _i32),
         ("alpha", _f32), ("beta", _f32), ("alpha_dev", _vp),
         ("ws", _vp), ("ws_bytes", _sz),
+        ("n_pairs", _i32), ("a_off", _i32 * 6), ("b_off", _i32 * 6),
     ]
 
 

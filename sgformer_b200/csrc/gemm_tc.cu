@@ -659,6 +659,8 @@ struct Params {
     int m, n, m_blocks, n_chunks, un;  // un = UMMA N (n rounded up to 16)
     int64_t kb_total;
     float* ws;  // [grid][un][m_blocks*128]
+    int n_pairs;                                  // partial products accumulated per node block (1, or the 6 of bf16x3)
+    int a_off[SGF_TN_MAX_PAIRS], b_off[SGF_TN_MAX_PAIRS];   // column offset (elements) of the plane each product reads
 };
 struct Tmaps {
     CUtensorMap a, b;
@@ -700,14 +702,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tn_kernel(const __grid_consta
         if (lane == 0) {
             const uint32_t stage_tx = (a_chunks + p.n_chunks) * CHUNK_BYTES;
             int stage = 0; uint32_t phase = 0;
+            // all partial products of a node block before the next block: the planes re-read by later products hit L2
             for (int64_t kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_arrive_expect_tx(&full[stage], stage_tx);
-                for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tm.a, &full[stage], c * 64, (int32_t)(kb * BKN));
-                for (int c = 0; c < p.n_chunks; ++c) tma_load_2d(sb + c * CHUNK_BYTES, &tm.b, &full[stage], c * 64, (int32_t)(kb * BKN));
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int pr = 0; pr < p.n_pairs; ++pr) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], stage_tx);
+                    for (int c = 0; c < a_chunks; ++c)
+                        tma_load_2d(sa + c * CHUNK_BYTES, &tm.a, &full[stage], p.a_off[pr] + c * 64, (int32_t)(kb * BKN));
+                    for (int c = 0; c < p.n_chunks; ++c)
+                        tma_load_2d(sb + c * CHUNK_BYTES, &tm.b, &full[stage], p.b_off[pr] + c * 64, (int32_t)(kb * BKN));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -715,23 +722,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tn_kernel(const __grid_consta
             const uint32_t idesc = make_idesc_bf16(128, p.un, 1, 1);  // both operands MN-major
             int stage = 0; uint32_t phase = 0;
             for (int64_t kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full[stage], phase);
-                tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
+                for (int pr = 0; pr < p.n_pairs; ++pr) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BKN / 16; ++k) {
-                    // MN-major SW128: LBO = stride between 64-element feature chunks, SBO = stride between 8-row node groups
-                    const uint64_t db = make_smem_desc_sw128(sb + k * 2048, CHUNK_BYTES, 1024);
-                    const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-                    for (int mb = 0; mb < p.m_blocks; ++mb) {
-                        const uint64_t da = make_smem_desc_sw128(sa + mb * 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
-                        umma_bf16(tmem_base + mb * 256, da, db, idesc, accum);
+                    for (int k = 0; k < BKN / 16; ++k) {
+                        // MN-major SW128: LBO = stride between 64-element feature chunks, SBO = stride between 8-row node groups
+                        const uint64_t db = make_smem_desc_sw128(sb + k * 2048, CHUNK_BYTES, 1024);
+                        const uint32_t accum = (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u;
+                        for (int mb = 0; mb < p.m_blocks; ++mb) {
+                            const uint64_t da = make_smem_desc_sw128(sa + mb * 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
+                            umma_bf16(tmem_base + mb * 256, da, db, idesc, accum);
+                        }
                     }
+                    umma_commit(&empty[stage]);
+                    if (kb == kb1 - 1 && pr == p.n_pairs - 1) umma_commit(tmem_full);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty[stage]);
-                if (kb == kb1 - 1) umma_commit(tmem_full);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -951,6 +960,16 @@ extern "C" int sgf_gemm_tn(const sgf_gemm_tn_args* a, void* stream) {
     p.n_chunks = (p.un + 63) / 64;
     p.kb_total = (a->rows + tn::BKN - 1) / tn::BKN;
     p.ws = (float*)a->ws;
+    if (a->n_pairs < 0 || a->n_pairs > SGF_TN_MAX_PAIRS) return SGF_ERR_ARG;
+    p.n_pairs = a->n_pairs > 0 ? a->n_pairs : 1;
+    int64_t a_span = a->m, b_span = a->n;      // columns the tensor maps must cover
+    for (int i = 0; i < p.n_pairs; ++i) {
+        p.a_off[i] = a->n_pairs > 0 ? a->a_off[i] : 0;
+        p.b_off[i] = a->n_pairs > 0 ? a->b_off[i] : 0;
+        if (p.a_off[i] < 0 || p.b_off[i] < 0 || p.a_off[i] % 64 || p.b_off[i] % 64) return SGF_ERR_ARG;
+        if (p.a_off[i] + a->m > a_span) a_span = p.a_off[i] + a->m;
+        if (p.b_off[i] + a->n > b_span) b_span = p.b_off[i] + a->n;
+    }
     const int mp = p.m_blocks * 128;
     int grid = 0;
     if (a->rows > 0) {
@@ -960,8 +979,8 @@ extern "C" int sgf_gemm_tn(const sgf_gemm_tn_args* a, void* stream) {
         tn::Tmaps tm;
         memset(&tm, 0, sizeof(tm));
         int rc;
-        if ((rc = make_tmap_bf16(&tm.a, a->a, a->rows, a->m, a->lda, tn::BKN))) return rc;
-        if ((rc = make_tmap_bf16(&tm.b, a->b, a->rows, a->n, a->ldb, tn::BKN))) return rc;
+        if ((rc = make_tmap_bf16(&tm.a, a->a, a->rows, a_span, a->lda, tn::BKN))) return rc;
+        if ((rc = make_tmap_bf16(&tm.b, a->b, a->rows, b_span, a->ldb, tn::BKN))) return rc;
         static bool attr_set = false;
         if (!attr_set) {
             SGF_CUDA_TRY(cudaFuncSetAttribute(tn::gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES));

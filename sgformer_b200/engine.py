@@ -116,7 +116,7 @@ def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precisi
     for hd in range(heads):
         kh, vh = k[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
         s_raw = torch.empty((m, d), dtype=torch.float32, device=dev)
-        K.gemm_tn(K.as_operand(kh, prec.planes), K.as_operand(vh, prec.planes), s_raw)
+        K.gemm_tn(K.as_operand(kh, prec.planes, memo=True), K.as_operand(vh, prec.planes, memo=True), s_raw)
         s_list.append(s_raw)
     comm.allreduce_(sq_q, z_raw, sq_k, *s_list)
     o = K.alloc_act(n_loc, heads * d, q.dtype, dev)
@@ -125,7 +125,7 @@ def attention_forward(q: Tensor, k: Tensor, v: Tensor, heads: int, prec: Precisi
     for hd in range(heads):
         qh, vh = q[:, hd * m:(hd + 1) * m], v[:, hd * d:(hd + 1) * d]
         bmat, btail, scal = K.attn_prepare_fwd(s_list[hd], z_raw[hd * m:(hd + 1) * m], sq_q, sq_k, prec.planes)
-        K.gemm_nt([K.as_operand(qh, prec.planes)], [bmat], [(0, 0, 0, 0, m)], d, o[:, hd * d:(hd + 1) * d],
+        K.gemm_nt([K.as_operand(qh, prec.planes, memo=True)], [bmat], [(0, 0, 0, 0, m)], d, o[:, hd * d:(hd + 1) * d],
                   epi=EPI_ATTN_APPLY, aux=vh, tail=btail, nf=float(n), den_out=den[hd])
     if tape is not None:
         tape.update(q=q, k=k, v=v, o=o, den=den, s=s_list, z=z_raw, scal=scal, heads=heads, m=m, d=d, n=n)
@@ -146,7 +146,7 @@ def attention_backward(tape: Tape, g: Tensor, gscale: float, prec: Precision, dq
         gnum, gden = K.attn_bwd_prep(g[:, hd * d:(hd + 1) * d], o[:, hd * d:(hd + 1) * d], den[hd], gscale)
         gnum_op = K.as_operand(gnum, prec.planes)
         ds_raw = torch.empty((m, d), dtype=torch.float32, device=dev)
-        K.gemm_tn(K.as_operand(qh, prec.planes), gnum_op, ds_raw)
+        K.gemm_tn(K.as_operand(qh, prec.planes, memo=True), gnum_op, ds_raw)
         dz_raw, _ = K.colstats(qh, w=gden, want_sumsq=False)
         part.append((gnum, gden, gnum_op, ds_raw, dz_raw))
     comm.allreduce_(*[t for p_ in part for t in (p_[3], p_[4])])
@@ -164,10 +164,10 @@ def attention_backward(tape: Tape, g: Tensor, gscale: float, prec: Precision, dq
         sb = scal_bwd[hd]
         K.gemm_nt([gnum_op], [b_dq], [(0, 0, 0, 0, d)], m, dq[:, hd * m:(hd + 1) * m], alpha_dev=sb[0:1], aux=qh, beta=1.0,
                   beta_dev=sb[1:2], r1_row=gden, r1_col=r1_col)
-        K.gemm_nt([K.as_operand(vh, prec.planes)], [b_dk], [(0, 0, 0, 0, d)], m, dk[:, hd * m:(hd + 1) * m], alpha_dev=sb[0:1],
+        K.gemm_nt([K.as_operand(vh, prec.planes, memo=True)], [b_dk], [(0, 0, 0, 0, d)], m, dk[:, hd * m:(hd + 1) * m], alpha_dev=sb[0:1],
                   aux=kh, beta=1.0, beta_dev=sb[2:3], bias=dk_bias)
         if dv is not None:
-            K.gemm_nt([K.as_operand(kh, prec.planes)], [b_dv], [(0, 0, 0, 0, m)], d, dv[:, hd * d:(hd + 1) * d],
+            K.gemm_nt([K.as_operand(kh, prec.planes, memo=True)], [b_dv], [(0, 0, 0, 0, m)], d, dv[:, hd * d:(hd + 1) * d],
                       alpha_dev=sb[0:1], aux=gnum, beta=float(n), accumulate=dv_accumulate)
 
 
@@ -213,7 +213,7 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
         qkv = torch.empty((n, K.ceil_to(nout, 8)), dtype=prec.act_dtype, device=dev)[:, :nout]
         csum = torch.zeros(nout, dtype=torch.float32, device=dev)
         csq = torch.zeros(nout, dtype=torch.float32, device=dev)
-        K.gemm_nt([K.as_operand(x, prec.planes)], [K.pack_operand(wcat, False, prec.planes)], [(0, 0, 0, 0, h)], nout, qkv,
+        K.gemm_nt([K.as_operand(x, prec.planes, memo=True)], [K.pack_operand(wcat, False, prec.planes)], [(0, 0, 0, 0, h)], nout, qkv,
                   bias=bcat, col_sum=csum, col_sumsq=csq)        # K^T 1, ||Q||^2, ||K||^2 fall out of the projection's epilogue
         q, k = qkv[:, :H * h], qkv[:, H * h:2 * H * h]
         v = qkv[:, 2 * H * h:] if use_weight else x
@@ -273,7 +273,7 @@ def trans_backward(P, cfg: dict, tape: Tape, dout: Tensor, gscale: float, prec: 
         K.gemm_nt([dqkv_op], [K.pack_operand(wcat, True, prec.planes)], [(0, 0, 0, 0, nout)], h, dprev,
                   accumulate=not first_write)
         dw = torch.empty((nout, h), dtype=torch.float32, device=dev)
-        K.gemm_tn(dqkv_op, K.as_operand(x_in, prec.planes), dw)
+        K.gemm_tn(dqkv_op, K.as_operand(x_in, prec.planes, memo=True), dw)
         dbias, _ = K.colstats(dqkv, want_sumsq=False)
         names = ["Wq", "Wk"] + (["Wv"] if use_weight else [])
         for j, nm in enumerate(names):
@@ -365,12 +365,12 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
         st = _stat_bufs(use_bn, training, h, dev)      # BatchNorm sums come out of the GEMM epilogue
         if use_init:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
-            z = K.gemm_nt([K.as_operand(y, prec.planes), K.as_operand(x0, prec.planes)], [w],
+            z = K.gemm_nt([K.as_operand(y, prec.planes, memo=True), K.as_operand(x0, prec.planes, memo=True)], [w],
                           [(0, 0, 0, 0, h), (1, 0, 0, h, h)], h, K.new_like(y), bias=P[f"{pfx}convs.{i}.W.bias"],
                           col_sum=st[0], col_sumsq=st[1])
         elif use_weight:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
-            z = K.gemm_nt([K.as_operand(y, prec.planes)], [w], [(0, 0, 0, 0, h)], h, K.new_like(y),
+            z = K.gemm_nt([K.as_operand(y, prec.planes, memo=True)], [w], [(0, 0, 0, 0, h)], h, K.new_like(y),
                           bias=P[f"{pfx}convs.{i}.W.bias"], col_sum=st[0], col_sumsq=st[1])
         else:
             z, st = y, (None, None)
@@ -427,9 +427,9 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
             dz_op = K.as_operand(dz, prec.planes)
             kin = 2 * h if use_init else h
             dw = torch.empty((h, kin), dtype=torch.float32, device=dev)
-            K.gemm_tn(dz_op, K.as_operand(L["y"], prec.planes), dw[:, :h])
+            K.gemm_tn(dz_op, K.as_operand(L["y"], prec.planes, memo=True), dw[:, :h])
             if use_init:
-                K.gemm_tn(dz_op, K.as_operand(x0, prec.planes), dw[:, h:])
+                K.gemm_tn(dz_op, K.as_operand(x0, prec.planes, memo=True), dw[:, h:])
             grads[wname] = dw
             grads[f"{pfx}convs.{i}.W.bias"] = colsum
             wt = _w(P, wname, prec, transpose=True)   # [kin, h]

@@ -66,6 +66,7 @@ class SGFormerFn(Function):
         """x: the rows this rank owns ([N, d_in], or its [N/P, d_in] block when `comm` is a row-sharding Comm)."""
         P = _pdict(names, params)
         need_tape = any(ctx.needs_input_grad)
+        K.operand_memo_begin()       # fp32 activations shared by several GEMMs of this step are packed once
         xin = E.input_operand(x, prec)
         seed = E.next_seed()
         tt, tg, th = (E.Tape(), E.Tape(), E.Tape()) if need_tape else (None, None, None)
@@ -81,6 +82,8 @@ class SGFormerFn(Function):
         logits = E.head_forward(P, cfg, feats, prec, th)
         if need_tape:
             ctx.state = (cfg, prec, graph, comm, names, params, tt, tg, th, x.requires_grad)
+        else:
+            K.operand_memo_clear()
         return logits
 
     @staticmethod
@@ -109,6 +112,7 @@ class SGFormerFn(Function):
             done = grads.get("__global__", ())
             comm.allreduce_(*[grads[n_] for n_ in names if n_ in grads and n_ not in done])
         ctx.state = None
+        K.operand_memo_clear()
         return (dx, None, None, None, None, None, None, *_grad_list(names, params, grads))
 
 

@@ -314,12 +314,36 @@ def pack_operand(src: Tensor, transpose: bool = False, planes: int = 1, colsum: 
     return Operand(dst, rows_out, cols_out, kp, planes)
 
 
-def as_operand(x: Tensor, planes: int) -> Operand:
-    """Activation -> operand: bf16 activations are used in place (planes=1); fp32 activations are packed."""
+# fp32 activations that feed several GEMMs of one step (q, k, v, the layer inputs, x0: forward product + weight gradient) are
+# packed into bf16x3 planes once: memo keyed by the tensor's storage, alive from the start of a forward to the end of its backward
+_operand_memo: Optional[dict] = None
+
+
+def operand_memo_begin():
+    global _operand_memo
+    _operand_memo = {}
+
+
+def operand_memo_clear():
+    global _operand_memo
+    _operand_memo = None
+
+
+def as_operand(x: Tensor, planes: int, memo: bool = False) -> Operand:
+    """Activation -> operand: bf16 activations are used in place (planes=1); fp32 activations are packed.
+    memo=True (forward activations that are never written again) reuses the packed planes within the step."""
     if x.dtype == torch.bfloat16:
         if planes != 1:
             raise ValueError("bf16 activations only form single-plane operands")
         return operand_from_bf16(x)
+    if memo and _operand_memo is not None:
+        key = (x.data_ptr(), tuple(x.shape), x.stride(), planes)
+        hit = _operand_memo.get(key)
+        if hit is not None:
+            return hit[1]
+        op = pack_operand(x, False, planes)
+        _operand_memo[key] = (x, op)          # holding x keeps its address from being reused while the entry lives
+        return op
     return pack_operand(x, False, planes)
 
 
@@ -411,7 +435,7 @@ def stats_fusable(out: Tensor) -> bool:
 
 
 def _tn_once(a: Tensor, lda: int, m: int, b: Tensor, ldb: int, n: int, rows: int, out: Tensor, transpose_out: bool,
-             alpha: float, beta: float, alpha_dev: Optional[Tensor]):
+             alpha: float, beta: float, alpha_dev: Optional[Tensor], pairs: Sequence[Tuple[int, int]] = ()):
     nbytes = C.c_size_t(0)
     check(lib().sgf_gemm_tn_ws_bytes(m, n, rows, C.byref(nbytes)), "sgf_gemm_tn_ws_bytes")
     ws = torch.empty(max(nbytes.value, 4), dtype=torch.uint8, device=out.device)
@@ -422,6 +446,9 @@ def _tn_once(a: Tensor, lda: int, m: int, b: Tensor, ldb: int, n: int, rows: int
     args.out, args.ldo, args.transpose_out = out.data_ptr(), out.stride(0), int(transpose_out)
     args.alpha, args.beta, args.alpha_dev = alpha, beta, _p(alpha_dev)
     args.ws, args.ws_bytes = ws.data_ptr(), nbytes.value
+    args.n_pairs = len(pairs)
+    for i, (ao, bo) in enumerate(pairs):
+        args.a_off[i], args.b_off[i] = ao, bo
     check(lib().sgf_gemm_tn(C.byref(args), _stream()), "sgf_gemm_tn")
 
 
@@ -437,17 +464,14 @@ def gemm_tn(A: Operand, B: Operand, out: Tensor, *, transpose_out: bool = False,
     exp = (B.k, A.k) if transpose_out else (A.k, B.k)
     if tuple(out.shape) != exp:
         raise ValueError(f"gemm_tn out is {tuple(out.shape)}, expected {exp}")
-    combos = _PAIRS3 if A.planes == 3 else [(0, 0)]
+    # bf16x3: the six partial products of a block accumulate inside ONE launch (plane column offsets, smallest terms first)
+    pairs = [(pa * A.kp, pb * B.kp) for pa, pb in _PAIRS3] if A.planes == 3 else []
     for m0 in range(0, A.k, 256):
         m = min(256, A.k - m0)
         for n0 in range(0, B.k, 256):
             n = min(256, B.k - n0)
             sub = out[n0:n0 + n, m0:m0 + m] if transpose_out else out[m0:m0 + m, n0:n0 + n]
-            for ci, (pa, pb) in enumerate(combos):
-                a_view = A.data[:, pa * A.kp + m0:]
-                b_view = B.data[:, pb * B.kp + n0:]
-                _tn_once(a_view, A.ld, m, b_view, B.ld, n, A.rows, sub, transpose_out, alpha,
-                         beta if ci == 0 else 1.0, alpha_dev)
+            _tn_once(A.data[:, m0:], A.ld, m, B.data[:, n0:], B.ld, n, A.rows, sub, transpose_out, alpha, beta, alpha_dev, pairs)
     return out
 
 

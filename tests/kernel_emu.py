@@ -88,7 +88,15 @@ def pack_operand(src, transpose=False, planes=1, colsum=None):
     return Operand(d, d.shape[0], d.shape[1], ceil_to(d.shape[1], 64), planes)
 
 
-def as_operand(x, planes):
+def operand_memo_begin():
+    pass
+
+
+def operand_memo_clear():
+    pass
+
+
+def as_operand(x, planes, memo=False):
     if x.dtype == torch.bfloat16:
         return operand_from_bf16(x)
     return pack_operand(x, False, planes)
