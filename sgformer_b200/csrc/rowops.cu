@@ -614,6 +614,43 @@ __global__ void __launch_bounds__(kRowBlock) pack_operand_kernel(const float* __
     }
 }
 
+// vector path of pack_operand for the common case (no transpose, no column sums, 8-column aligned): a thread converts 8
+// consecutive columns with two 16-byte loads and one 16-byte store per plane
+__global__ void __launch_bounds__(kRowBlock) pack_rows_vec_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                                                   __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int kp,
+                                                                   int64_t plane_ld, const int64_t* __restrict__ row_index) {
+    const int cpr = kp >> 3;                                  // 8-column chunks per output row
+    const int64_t total = rows * cpr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t r = t / cpr;
+        const int c = (int)(t - r * cpr) << 3;
+        float v[8];
+        if (c < cols) {                                       // cols % 8 == 0: a chunk is entirely inside or outside
+            const float4* sp = reinterpret_cast<const float4*>(src + (row_index ? row_index[r] : r) * ld_src + c);
+            const float4 a = __ldg(sp), b = __ldg(sp + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        __nv_bfloat16* o = dst + r * ld_dst + c;
+        *reinterpret_cast<uint4*>(o) = Vec16<__nv_bfloat16>::pack(v);
+        if (plane_ld > 0) {
+            float r1[8], r2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat16 p0 = __float2bfloat16_rn(v[i]);
+                r1[i] = v[i] - __bfloat162float(p0);
+                const __nv_bfloat16 p1 = __float2bfloat16_rn(r1[i]);
+                r2[i] = r1[i] - __bfloat162float(p1);
+            }
+            *reinterpret_cast<uint4*>(o + plane_ld) = Vec16<__nv_bfloat16>::pack(r1);
+            *reinterpret_cast<uint4*>(o + 2 * plane_ld) = Vec16<__nv_bfloat16>::pack(r2);
+        }
+    }
+}
+
 // multi-head attention backward: the norm-gradient scalar is shared by all heads (one ||q||_F over [N,H,M])
 __global__ void attn_combine_scal_kernel(float* __restrict__ scal_bwd, int heads, int stride, const float* __restrict__ scal_fwd) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1027,8 +1064,14 @@ extern "C" int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, 
     if (kp < cols_out || (plane_ld > 0 && plane_ld < kp) || ld_dst < (plane_ld > 0 ? 2 * plane_ld + kp : kp)) return SGF_ERR_ARG;
     if (colsum && cols > 8192) return SGF_ERR_UNSUPPORTED;
     const int64_t rows_out = transpose ? cols : rows;
-    pack_operand_kernel<<<ew_grid(rows_out * kp), kRowBlock, colsum ? cols * sizeof(float) : 0, (cudaStream_t)stream>>>(
-        src, ld_src, rows, cols, transpose, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, colsum, row_index);
+    const bool vec = !transpose && !colsum && cols % 8 == 0 && kp % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 &&
+                     plane_ld % 8 == 0 && aligned16(src) && aligned16(dst);
+    if (vec)
+        pack_rows_vec_kernel<<<ew_grid(rows_out * (kp / 8)), kRowBlock, 0, (cudaStream_t)stream>>>(
+            src, ld_src, rows, cols, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, row_index);
+    else
+        pack_operand_kernel<<<ew_grid(rows_out * kp), kRowBlock, colsum ? cols * sizeof(float) : 0, (cudaStream_t)stream>>>(
+            src, ld_src, rows, cols, transpose, (__nv_bfloat16*)dst, ld_dst, kp, plane_ld, colsum, row_index);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }
