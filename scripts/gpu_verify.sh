@@ -1,3 +1,6 @@
+# Round-end verification on one B200 (what the driver runs, plus the numbers quoted in DESIGN.md / profiles):
+#   GPU tests, smoke(), default bench (with cpu_baseline + e2e), the reference arm, launch list of the products step,
+#   the other BASELINE shapes, preprocessing / evaluation kernels at the products shape.
 set +e
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out; mkdir -p $OUT
@@ -10,3 +13,10 @@ grep -E "passed|failed" $OUT/all_gpu.log; grep -E "^(FAILED|E   [A-Za-z])" $OUT/
 tail -n 2 $OUT/smoke.log
 grep "^{" $OUT/bench_default.log
 grep "^{" $OUT/bench_reference.log | cut -c1-600
+for WL in arxiv pokec papers100M-minibatch; do
+  timeout 300 python bench.py --workload $WL --no-cpu-baseline --no-e2e --steps 20 --warmup 5 > $OUT/bench_$WL.log 2>&1; echo "bench $WL rc=$?"
+  grep "^{" $OUT/bench_$WL.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$WL ms_per_step', d['ms_per_step'], 'nodes/s', d['value'])"
+done
+timeout 300 python bench.py --rmat --no-cpu-baseline --no-e2e --steps 5 --warmup 3 > $OUT/bench_products_rmat.log 2>&1; echo "bench rmat rc=$?"
+grep "^{" $OUT/bench_products_rmat.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('rmat ms_per_step', d['ms_per_step'], 'spmm', d['roofline']['avg_launch_ms'], d['roofline']['frac'])"
+timeout 600 python scripts/bench_prep.py 2>&1 | tee $OUT/prep_products.log
