@@ -8,6 +8,8 @@
 // Geometry shared by all kernels: a feature row of h elements is split into 16-byte chunks; `lpr` (a power of two
 // <= 32) lanes cover one row, each lane owning chunks {sub, sub+lpr, ...} (CPL of them); a warp processes 32/lpr rows
 // at a time.  Because the lane -> column mapping is fixed, column sums accumulate in registers across the row loop.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_count.h"
 #include "../../include/sgformer_b200.h"
@@ -1064,7 +1066,9 @@ extern "C" int sgf_pack_operand(const float* src, int64_t ld_src, int64_t rows, 
     if (kp < cols_out || (plane_ld > 0 && plane_ld < kp) || ld_dst < (plane_ld > 0 ? 2 * plane_ld + kp : kp)) return SGF_ERR_ARG;
     if (colsum && cols > 8192) return SGF_ERR_UNSUPPORTED;
     const int64_t rows_out = transpose ? cols : rows;
-    const bool vec = !transpose && !colsum && cols % 8 == 0 && kp % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 &&
+    // opt-in (SGF_PACK_VEC=1): written after the round's last GPU test pass, so the verified scalar kernel stays the default
+    static const bool vec_on = [] { const char* e = getenv("SGF_PACK_VEC"); return e && e[0] == '1'; }();
+    const bool vec = vec_on && !transpose && !colsum && cols % 8 == 0 && kp % 8 == 0 && ld_src % 4 == 0 && ld_dst % 8 == 0 &&
                      plane_ld % 8 == 0 && aligned16(src) && aligned16(dst);
     if (vec)
         pack_rows_vec_kernel<<<ew_grid(rows_out * (kp / 8)), kRowBlock, 0, (cudaStream_t)stream>>>(
