@@ -159,36 +159,6 @@ __device__ __forceinline__ void store32(void* base, int dtype, int64_t off, bool
         for (int j = 0; j < 32; ++j) if (j < nv) store1(base, dtype, off + j, f[j]);
     }
 }
-// 8 consecutive elements starting at element offset `off` (vec: 16-byte aligned and all 8 valid; else the first nv, rest 0)
-__device__ __forceinline__ void load8(const void* base, int dtype, int64_t off, bool vec, int nv, float* f) {
-    if (vec) {
-        if (dtype == 1) {
-            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off), f);
-        } else {
-            const uint4* q = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + off);
-            Vec16<float>::unpack(q[0], f);
-            Vec16<float>::unpack(q[1], f + 4);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = j < nv ? load1(base, dtype, off + j) : 0.f;
-    }
-}
-__device__ __forceinline__ void store8(void* base, int dtype, int64_t off, bool vec, int nv, const float* f) {
-    if (vec) {
-        if (dtype == 1) {
-            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off) = Vec16<__nv_bfloat16>::pack(f);
-        } else {
-            uint4* q = reinterpret_cast<uint4*>(static_cast<float*>(base) + off);
-            q[0] = Vec16<float>::pack(f);
-            q[1] = Vec16<float>::pack(f + 4);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < nv) store1(base, dtype, off + j, f[j]);
-    }
-}
-
 // The three warp roles walk the CTA's tiles in the same order.
 //  streaming:  tile = blockIdx.x + i*gridDim.x over (m_blk, n_blk) pairs, n_blk fastest.
 //  resident-B: the CTA owns row tiles m = blockIdx.x + i*gridDim.x; they are visited in chunks of p.chunk, and inside a chunk
