@@ -156,9 +156,85 @@ def graphconv_layer_cases():
     print("graphconv_layer", list(out))
 
 
+def import_reference_driver_modules():
+    """`data_utils` (eval_acc) and `eval` (evaluate) of the reference's large/ directory, through the shims, unmodified."""
+    import importlib
+    from _refload import REF_ROOT, SHIMS
+    for name in ("data_utils", "eval", "dataset", "logger", "parse", "ours", "gnns"):
+        sys.modules.pop(name, None)
+    saved = list(sys.path)
+    sys.path[:0] = [SHIMS, os.path.join(REF_ROOT, "large")]
+    try:
+        du = importlib.import_module("data_utils")
+        ev = importlib.import_module("eval")
+    finally:
+        sys.path[:] = saved
+    return du, ev
+
+
+def evaluate_cases():
+    """The reference's own evaluate() / eval_acc (large/eval.py:6-33, large/data_utils.py:210-220) on fixed logits: pins K11
+    (sgf_eval_acc) and sgformer_b200.eval.evaluate."""
+    from types import SimpleNamespace
+    du, ev = import_reference_driver_modules()
+    out = {}
+    for name, (n, c, seed, ties) in {"c7": (500, 7, 0, 0), "c47_ties": (1500, 47, 1, 200), "c2": (257, 2, 2, 40)}.items():
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(n, c, generator=g)
+        if ties:
+            rows = torch.randperm(n, generator=g)[:ties]
+            logits[rows, (rows % c)] = logits[rows].max(dim=1).values      # exact ties with the row maximum
+        label = torch.randint(0, c, (n, 1), generator=g)
+        perm = torch.randperm(n, generator=g)
+        split = {"train": perm[: n // 2], "valid": perm[n // 2: 3 * n // 4], "test": perm[3 * n // 4:]}
+
+        class Fixed(torch.nn.Module):
+            def forward(self, x, ei):
+                return logits.clone()
+
+        ds = SimpleNamespace(graph={"node_feat": torch.zeros(n, 1), "edge_index": torch.zeros(2, 0, dtype=torch.long)}, label=label)
+        tr, va, te, vloss, lsm = ev.evaluate(Fixed(), ds, split, du.eval_acc, torch.nn.NLLLoss(), SimpleNamespace(dataset="synthetic"))
+        out[name] = dict(logits=logits, label=label, split=split, train_acc=tr, valid_acc=va, test_acc=te, valid_loss=float(vloss),
+                         log_softmax=lsm)
+    torch.save(out, os.path.join(GOLD, "evaluate.pt"))
+    print("evaluate", {k: (v["train_acc"], v["valid_acc"], v["test_acc"], v["valid_loss"]) for k, v in out.items()})
+
+
+def graph_prep_cases():
+    """to_undirected / remove_self_loops / add_self_loops of the torch_geometric restatement the reference drivers run through
+    here (tests/ref_shims; the real package is not installable - SURVEY.md 8c): fixtures for K10."""
+    from _refload import SHIMS
+    saved = list(sys.path)
+    sys.path.insert(0, SHIMS)
+    try:
+        from torch_geometric.utils import add_self_loops, remove_self_loops, to_undirected
+    finally:
+        sys.path[:] = saved
+    out = {}
+    for name, (n, e, seed, loops, dup) in {"small": (9, 30, 0, 4, 5), "mid": (400, 3000, 1, 60, 200), "isolated": (50, 40, 2, 0, 0),
+                                           "hub": (3000, 9000, 3, 10, 0)}.items():
+        g = torch.Generator().manual_seed(seed)
+        hi = n if name != "isolated" else n // 2
+        ei = torch.stack([torch.randint(0, hi, (e,), generator=g), torch.randint(0, hi, (e,), generator=g)])
+        if name == "hub":
+            ei[1, :5000] = 7
+        ei[1, :loops] = ei[0, :loops]
+        if dup:
+            ei = torch.cat([ei, ei[:, :dup]], 1)
+        und = to_undirected(ei, num_nodes=n)
+        nsl, _ = remove_self_loops(und)
+        full, _ = add_self_loops(nsl, num_nodes=n)
+        out[name] = dict(n=n, edge_index=ei, to_undirected=und, remove_self_loops_raw=remove_self_loops(ei)[0],
+                         add_self_loops_raw=add_self_loops(ei, num_nodes=n)[0], prepared=full)
+    torch.save(out, os.path.join(GOLD, "graph_prep.pt"))
+    print("graph_prep", {k: tuple(v["prepared"].shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     for nm, sp in CASES.items():
         model_case(nm, sp)
     attention_cases()
     graphconv_layer_cases()
+    evaluate_cases()
+    graph_prep_cases()

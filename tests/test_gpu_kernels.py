@@ -175,6 +175,14 @@ def test_eval_acc_matches_reference_semantics(K, rows, c, m):
     assert acc_all == np_ref.eval_acc(labels.numpy(), logits.numpy())
 
 
+def test_eval_and_graph_prep_match_reference_fixtures(K):
+    """K10 / K11 against tests/golden/{graph_prep,evaluate}.pt (the reference's own evaluate()/eval_acc; PyG-semantics preprocessing)."""
+    from fixture_checks import check_evaluate_fixture, check_graph_prep_fixture
+    dev = lambda t: t.to(DEV)      # noqa: E731
+    check_evaluate_fixture(lambda lg, lb, idx, want: K.eval_acc(lg, lb, idx, want_loss=want), to_dev=dev)
+    check_graph_prep_fixture(K.to_undirected, K.remove_self_loops, K.add_self_loops, to_dev=dev)
+
+
 def test_csr_subset_matches_subgraph_then_build(K):
     """K9 on the CSR == PyG-semantics subgraph (sgf_subgraph) followed by a CSR build, bit-exactly; node_map is restored."""
     from sgformer_b200.graph import Graph

@@ -115,3 +115,26 @@ def test_eval_acc_known_answer():
     out = torch.tensor([[0.9, 0.1, 0.0, 0.0], [0.8, 0.1, 0.1, 0.0], [0.0, 0.1, 0.9, 0.0], [0.0, 0.1, 0.1, 0.8]])
     y = torch.tensor([0, 1, 2, 3])
     assert int((out.argmax(1) == y).sum()) == 3
+
+
+def test_oracle_eval_and_graph_prep_against_reference_fixtures():
+    """oracle/np_ref.py (eval_acc, to_undirected, remove/add_self_loops) against fixtures produced by the reference's own
+    evaluate()/eval_acc and by the torch_geometric restatement its drivers ran through (tests/make_golden.py)."""
+    import numpy as np
+
+    from fixture_checks import check_evaluate_fixture, check_graph_prep_fixture
+    from oracle import np_ref
+
+    def eval_fn(logits, label, idx, want_loss):
+        acc = np_ref.eval_acc(label[idx].numpy(), logits[idx].numpy())
+        loss = None
+        if want_loss:
+            lsm = torch.log_softmax(logits, 1)
+            loss = float(torch.nn.functional.nll_loss(lsm[idx], label.squeeze(1)[idx]))
+        return acc, loss
+
+    check_evaluate_fixture(eval_fn)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))      # noqa: E731
+    check_graph_prep_fixture(lambda ei, n: t(np_ref.to_undirected(ei.numpy(), n)),
+                             lambda ei: t(np_ref.remove_self_loops(ei.numpy())),
+                             lambda ei, n: t(np_ref.add_self_loops(ei.numpy(), n)))
