@@ -5,7 +5,7 @@ the others back the standalone modules/functions of the reference surface (Trans
 full_attention_conv, GraphConvLayer's SpMM, nn.Linear on the tensor-core GEMM)."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 from torch.autograd import Function
