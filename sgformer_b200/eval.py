@@ -28,10 +28,11 @@ def evaluate(model, dataset, split_idx, eval_func, criterion, args, result=None)
         model.eval()
         out = model(dataset.graph['node_feat'], dataset.graph['edge_index'])
     label = dataset.label
-    on_device = (out.is_cuda and getattr(eval_func, "__name__", "") == "eval_acc" and label.dim() == 2 and label.shape[1] == 1
+    on_device = (getattr(eval_func, "__name__", "") == "eval_acc" and label.dim() == 2 and label.shape[1] == 1
                  and label.dtype == torch.int64 and getattr(args, "dataset", None) not in _BCE_DATASETS)
     if not on_device:
-        # the reference's own host-side path (large/eval.py:13-31), unchanged
+        # other metrics (rocauc, f1: sklearn on the host in the reference) and the multi-label datasets: the caller's own
+        # eval_func / criterion, exactly as large/eval.py:13-31 - these are outside the accelerated path, not a fallback of K11
         train_acc = eval_func(label[split_idx['train']], out[split_idx['train']])
         valid_acc = eval_func(label[split_idx['valid']], out[split_idx['valid']])
         test_acc = eval_func(label[split_idx['test']], out[split_idx['test']])
@@ -43,7 +44,9 @@ def evaluate(model, dataset, split_idx, eval_func, criterion, args, result=None)
             valid_loss = criterion(out[split_idx['valid']], label.squeeze(1)[split_idx['valid']])
         return train_acc, valid_acc, test_acc, valid_loss, out
     logits = out.float()
-    lab = label.to(out.device)
+    if not logits.is_cuda:              # logits handed in from the host (e.g. `result=` of evaluate_large): K11 has no CPU path
+        logits = logits.cuda()
+    lab = label.to(logits.device)
     train_acc, _ = K.eval_acc(logits, lab, split_idx['train'])
     valid_acc, valid_loss = K.eval_acc(logits, lab, split_idx['valid'], want_loss=True)
     test_acc, _ = K.eval_acc(logits, lab, split_idx['test'])
