@@ -68,3 +68,21 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f"{f} imports oracle/"
                 assert "kernel_emu" not in text, f"{f} references the test-only kernel emulation"
+
+
+def test_wrappers_around_the_model_fail_loudly_without_cuda():
+    """K10 / K11 wrappers (pyg_utils, eval, kernels.eval_acc) have no CPU path: CPU tensors raise instead of falling back."""
+    import pytest
+    import torch
+
+    from sgformer_b200 import kernels as K
+    from sgformer_b200 import pyg_utils as U
+
+    ei = torch.tensor([[0, 1, 2], [1, 1, 0]])
+    for call in (lambda: U.to_undirected(ei, num_nodes=3), lambda: U.remove_self_loops(ei), lambda: U.add_self_loops(ei, num_nodes=3),
+                 lambda: U.subgraph(torch.tensor([0, 1]), ei, relabel_nodes=True, num_nodes=3),
+                 lambda: K.eval_acc(torch.zeros(3, 2), torch.zeros(3, 1, dtype=torch.long))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    with pytest.raises(NotImplementedError):
+        U.remove_self_loops(ei, torch.zeros(3))
