@@ -92,11 +92,13 @@ int sgf_add_self_loops(const int64_t* edge_index, int64_t nnz, int64_t n, int64_
  * = positions in subset, sorted; dinv from the induced in-degrees) — the structure GraphConv needs for a mini-batch, in
  * O(sum of the subset rows' lengths) instead of PyG subgraph's O(E) mask per batch + a CSR rebuild.
  * node_map: int32 [n] scratch that must hold -1 everywhere on entry and is restored to -1 on exit (kept across batches).
- * out_col_capacity >= sum of the subset rows' lengths is always enough. */
+ * out_col_capacity >= sum of the subset rows' lengths is always enough.  A smaller capacity never overruns out_col: the row
+ * pointers are clamped to it (the tail rows come out truncated / empty) and *out_needed (device int64, nullable) receives the
+ * induced nnz the full result needs, so the caller can detect out_needed > out_col_capacity without a sync per batch. */
 int sgf_csr_subset_ws_bytes(int64_t n_sub, int64_t max_out_nnz, size_t* bytes);
 int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* subset, int64_t n_sub,
                    int32_t* node_map, int64_t* out_rowptr /* [n_sub+1] */, int32_t* out_col, int64_t out_col_capacity,
-                   float* dinv /* [n_sub] or NULL */, void* ws, size_t ws_bytes, void* stream);
+                   float* dinv /* [n_sub] or NULL */, int64_t* out_needed, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K6 / K7 — CSR SpMM (replaces torch_sparse.matmul(adj, x), large/ours.py:34, 100M/ours.py:80, and its
@@ -133,6 +135,10 @@ int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, in
  * single B source; used for the attention normaliser column.  n_out (+16) <= 272 per n-block of 256. */
 #define SGF_EPI_AFFINE 0      /* out = (alpha*acc + beta*aux[r,c] + bias[c] + r1_row[r]*r1_col[c]) -> relu -> *row_scale[r] (+= out) */
 #define SGF_EPI_ATTN_APPLY 1  /* out[r,c] = (acc[r,c] + nf*aux[r,c]) / (acc_tail[r,0] + nf); den_out[r] = that denominator */
+#define SGF_EPI_ATTN_GRAM 2   /* out[r,c] = (acc[r,c] + bias[c]) / (acc_tail[r,0] + *nf_dev); den_out[r] = that denominator.
+                               * Pass 2 of the Gram-form attention (sgf_attn_gram_prepare_fwd): projections, q~.(k~^T v) + N v,
+                               * normaliser and divide of full_attention_conv (medium/ours.py:76-85,16-34) as ONE GEMM of the
+                               * layer input */
 
 #define SGF_GEMM_AUTO 0
 #define SGF_GEMM_STREAM_B 1
@@ -154,6 +160,7 @@ typedef struct {
     const float* alpha_dev; const float* beta_dev; /* optional device scalars multiplied into alpha/beta */
     int32_t relu, accumulate;
     float nf;                                   /* ATTN_APPLY: node count N as float */
+    const float* nf_dev;                        /* ATTN_GRAM: device scalar added to the tail column (replaces nf) */
     float* den_out;                             /* ATTN_APPLY: [rows] fp32 or NULL */
     const float* r1_row; const float* r1_col;   /* AFFINE: optional rank-1 term + r1_row[r]*r1_col[c] (both or neither) */
     float* col_sum; float* col_sumsq;           /* optional (caller-zeroed, fp32 [n_out]): column sums / sums of squares of the
@@ -299,6 +306,57 @@ int sgf_attn_prepare_bwd(const float* s_raw, const float* z_raw, const float* ds
                          const float* scal_fwd, int m, int d, void* b_dq, int64_t ld_b_dq, void* b_dv, int64_t ld_b_dv,
                          void* b_dk, int64_t ld_b_dk, int64_t plane_ld_d, int64_t plane_ld_m, float* r1_col,
                          float* dk_bias, float* scal_bwd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gram-form linear attention (single head): TransConvLayer.forward = Wq/Wk/Wv projections + full_attention_conv + its
+ * autograd (medium/ours.py:14-34,76-95; large/ours.py:123-157; 100M/ours.py:12-43,175-190) WITHOUT materialising q, k, v.
+ * Every node contraction of the layer is a function of G = x^T x and s = x^T 1 of the layer input x [N,h] (derivation at the
+ * top of csrc/attn_gram.cu), so the layer is:   pass 1  G, s            (sgf_gemm_tn x^T x + sgf_colstats)
+ *                                               h x h   sgf_attn_gram_prepare_fwd
+ *                                               pass 2  out = (x Bt^T + bt) / (x ct + dt)     (sgf_gemm_nt, SGF_EPI_ATTN_GRAM)
+ * and its backward:  sgf_ln_bwd_attn (row prologue) -> P = x^T gnum' (sgf_gemm_tn) -> sgf_attn_gram_prepare_bwd ->
+ *                    dx = [gnum' | x] . [Bt | A3] + gden' (x) ct + a4 (sgf_gemm_nt, two segments).
+ * All pointers are DEVICE fp32, row-major and dense unless a pitch is given.  use_weight=False (V = x, medium/ours.py:84) is
+ * expressed by passing the identity as wv and zeros as bv.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t h, m, d;            /* input width, q/k width (Wq, Wk: [m,h]), v width (Wv: [d,h]) */
+    int64_t n_nodes;            /* N of `N*vs` / `+N` (medium/ours.py:25,31): the GLOBAL node count when row-sharded */
+    const float *wq, *bq, *wk, *bk, *wv, *bv;
+    int64_t ld_wq, ld_wk, ld_wv;
+    const float* G;             /* [h,h] x^T x (all-reduced over the row shards) */
+    const float* s;             /* [h]   x^T 1 */
+    /* written by prepare_fwd, read again by prepare_bwd */
+    float *kx, *qx, *vx;        /* [m,h], [m,h], [d,h]: k^T x, q^T x, v^T x */
+    float *z1, *q1, *v1;        /* [m], [m], [d]:       k^T 1, q^T 1, v^T 1 */
+    float* S;                   /* [m,d] k^T v */
+    float* Bt;                  /* [d,h]  B operand of the apply GEMM (K-major over h), before bf16 packing */
+    float* tail;                /* [16,h] caller-zeroed; row 0 = ct */
+    float* bt;                  /* [d] */
+    float* sc;                  /* [16] scalars: 0 ||q||^2, 1 ||k||^2, 2 alpha, 3 beta = alpha/N, 4 dt, 5 N, 6 1.0, 7 bq.z1,
+                                   8 <dS,S>+<dz,z1>, 9 c, 10 -c/||q||^2, 11 -c/||k||^2 */
+    /* prepare_bwd only */
+    const float* P;             /* [h,d] x^T gnum' */
+    const float* pg;            /* [h]   x^T gden' */
+    const float* cs;            /* [d]   1^T gnum' */
+    const float* sg;            /* [1]   1^T gden' */
+    float *dwq, *dbq, *dwk, *dbk, *dwv, *dbv;   /* gradients, shapes of the parameters (dense) */
+    float* bcat;                /* [h, d+h] = [Bt^T | A3]: B operand of dx = gnum' Bt + x A3 */
+    float* a4;                  /* [h] constant row of dx */
+    float* ws; int64_t ws_floats;   /* scratch, sgf_attn_gram_ws_floats */
+} sgf_attn_gram_args;
+int sgf_attn_gram_ws_floats(int h, int m, int d, int64_t* n_floats /* host out */);
+int sgf_attn_gram_prepare_fwd(const sgf_attn_gram_args* args /* host */, void* stream);
+int sgf_attn_gram_prepare_bwd(const sgf_attn_gram_args* args /* host */, void* stream);
+/* LayerNorm backward of y = dropout(relu?(LN?(a*o + b*r))) (TransConv.forward, large/ours.py:208-216) fused with the row
+ * prologue of the attention backward: with du the gradient w.r.t. u = a*o + b*r (as sgf_ln_bwd) and ga = a*du,
+ *   gnum[r,:] = ga/den[r],  gden[r] = -(ga . o[r,:])/den[r],  dr (nullable) = b*du,
+ *   cs[c] += gnum[r,c],  pg[c] += xa[r,c]*gden[r],  sg[0] += gden[r]      (fp32, caller-zeroed),
+ * dgamma/dbeta as sgf_ln_bwd.  o = attention output, den = SGF_EPI_ATTN_GRAM's den_out, xa = the layer input (may alias r). */
+int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, const void* xa, int64_t ld, int64_t rows, int h, int dtype,
+                    float a, float b, const float* gamma, const float* beta, const float* stats, int use_ln, int use_relu,
+                    float p, uint64_t seed, float gscale, const float* den, void* gnum, float* gden, void* dr, float* dgamma,
+                    float* dbeta, float* cs, float* pg, float* sg, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ from . import _build
 _i32, _i64, _f32, _u64, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_size_t
 SGF_MAX_SRC, SGF_MAX_SEG = 4, 16
 F32, BF16 = 0, 1
-EPI_AFFINE, EPI_ATTN_APPLY = 0, 1
+EPI_AFFINE, EPI_ATTN_APPLY, EPI_ATTN_GRAM = 0, 1, 2
 
 
 class GemmNtArgs(C.Structure):
@@ -30,11 +30,28 @@ class GemmNtArgs(C.Structure):
         ("alpha", _f32), ("beta", _f32),
         ("alpha_dev", _vp), ("beta_dev", _vp),
         ("relu", _i32), ("accumulate", _i32),
-        ("nf", _f32),
+        ("nf", _f32), ("nf_dev", _vp),
         ("den_out", _vp),
         ("r1_row", _vp), ("r1_col", _vp),
         ("col_sum", _vp), ("col_sumsq", _vp),
         ("schedule", _i32),
+    ]
+
+
+class AttnGramArgs(C.Structure):
+    """sgf_attn_gram_args (include/sgformer_b200.h): every pointer is device fp32."""
+    _fields_ = [
+        ("h", _i32), ("m", _i32), ("d", _i32), ("n_nodes", _i64),
+        ("wq", _vp), ("bq", _vp), ("wk", _vp), ("bk", _vp), ("wv", _vp), ("bv", _vp),
+        ("ld_wq", _i64), ("ld_wk", _i64), ("ld_wv", _i64),
+        ("G", _vp), ("s", _vp),
+        ("kx", _vp), ("qx", _vp), ("vx", _vp), ("z1", _vp), ("q1", _vp), ("v1", _vp), ("S", _vp),
+        ("Bt", _vp), ("tail", _vp), ("bt", _vp), ("sc", _vp),
+        # backward
+        ("P", _vp), ("pg", _vp), ("cs", _vp), ("sg", _vp),
+        ("dwq", _vp), ("dbq", _vp), ("dwk", _vp), ("dbk", _vp), ("dwv", _vp), ("dbv", _vp),
+        ("bcat", _vp), ("a4", _vp),
+        ("ws", _vp), ("ws_floats", _i64),
     ]
 
 
@@ -74,6 +91,11 @@ _SIGS = {
                              _u64, _vp, _vp, _vp]),
     "sgf_ln_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, C.c_int, C.c_int,
                              _f32, _u64, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "sgf_ln_bwd_attn": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, C.c_int, C.c_int,
+                                  _f32, _u64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgf_attn_gram_ws_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_i64)]),
+    "sgf_attn_gram_prepare_fwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
+    "sgf_attn_gram_prepare_bwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
     "sgf_bn_finalize": (C.c_int, [_vp, _vp, _i64, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgf_bn_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                              _f32, _u64, _f32, _vp, _vp, _vp, _vp]),
@@ -85,7 +107,7 @@ _SIGS = {
                             _vp]),
     "sgf_pack_operand": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, _vp, _i64, C.c_int, _i64, _vp, _vp, _vp]),
     "sgf_csr_subset_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
-    "sgf_csr_subset": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "sgf_csr_subset": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "sgf_eval_acc": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp]),
     "sgf_softmax_nll": (C.c_int, [_vp, _i64, _vp, _vp, _i64, C.c_int, _f32, _vp, _vp, _i64, _vp]),
     "sgf_head_mean": (C.c_int, [_vp, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp]),

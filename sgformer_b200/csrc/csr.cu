@@ -346,6 +346,16 @@ __global__ void subset_count_kernel(const int64_t* __restrict__ rowptr, const in
         if (lane == 0) counts[i] = c;
     }
 }
+// The caller's out_col holds `capacity` entries (a no-sync bound on the induced nnz): clamp the scanned row pointers to it so
+// that the fill / sort / degree kernels never touch memory past the buffer, and report the true total so the host can tell.
+__global__ void subset_clamp_kernel(int64_t* __restrict__ out_rowptr, int64_t n_sub, int64_t capacity, int64_t* __restrict__ needed) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_sub; i += stride) {
+        const int64_t v = out_rowptr[i];
+        if (i == n_sub && needed) *needed = v;
+        if (v > capacity) out_rowptr[i] = capacity;
+    }
+}
 __global__ void subset_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                    const int64_t* __restrict__ subset, int64_t n_sub, int64_t n,
                                    const int32_t* __restrict__ node_map, const int64_t* __restrict__ out_rowptr,
@@ -357,12 +367,14 @@ __global__ void subset_fill_kernel(const int64_t* __restrict__ rowptr, const int
         const int64_t v = subset[i];
         if (v < 0 || v >= n) continue;
         int64_t w = out_rowptr[i];
+        const int64_t lim = out_rowptr[i + 1];      // == w + induced row length unless clamped to the buffer capacity
         const int64_t s = rowptr[v], e = rowptr[v + 1];
-        for (int64_t base = s; base < e; base += 32) {
+        for (int64_t base = s; base < e && w < lim; base += 32) {
             const int64_t j = base + lane;
             const int32_t m = j < e ? node_map[col[j]] : -1;
             const unsigned keep = __ballot_sync(0xffffffffu, m >= 0);
-            if (m >= 0) out_col[w + __popc(keep & ((1u << lane) - 1u))] = m;
+            const int64_t pos = w + __popc(keep & ((1u << lane) - 1u));
+            if (m >= 0 && pos < lim) out_col[pos] = m;
             w += __popc(keep);
         }
     }
@@ -620,13 +632,15 @@ extern "C" int sgf_csr_subset_ws_bytes(int64_t n_sub, int64_t max_out_nnz, size_
 
 extern "C" int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t n, const int64_t* subset, int64_t n_sub,
                               int32_t* node_map, int64_t* out_rowptr, int32_t* out_col, int64_t out_col_capacity, float* dinv,
-                              void* ws, size_t ws_bytes, void* stream) {
-    if (!rowptr || n < 0 || n_sub < 0 || !node_map || !out_rowptr || !ws || (n_sub > 0 && !subset)) return SGF_ERR_ARG;
+                              int64_t* out_needed, void* ws, size_t ws_bytes, void* stream) {
+    if (!rowptr || n < 0 || n_sub < 0 || !node_map || !out_rowptr || !ws || (n_sub > 0 && !subset) || out_col_capacity < 0)
+        return SGF_ERR_ARG;
     CsrWs w = carve_ws(ws, out_col_capacity, n_sub);
     if (ws_bytes < w.bytes) return SGF_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_sub == 0) {
         SGF_CUDA_TRY(cudaMemsetAsync(out_rowptr, 0, 8, st));
+        if (out_needed) SGF_CUDA_TRY(cudaMemsetAsync(out_needed, 0, 8, st));
         return SGF_OK;
     }
     SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
@@ -637,6 +651,8 @@ extern "C" int sgf_csr_subset(const int64_t* rowptr, const int32_t* col, int64_t
     SGF_LAUNCH_CHECK(); count_launch();
     int rc = launch_scan(w.counts, n_sub, 0, out_rowptr, w.block_sums, w.total, w.cursor, st);
     if (rc) return rc;
+    subset_clamp_kernel<<<grid_for(n_sub + 1, 256), 256, 0, st>>>(out_rowptr, n_sub, out_col_capacity, out_needed);
+    SGF_LAUNCH_CHECK(); count_launch();
     subset_fill_kernel<<<grid_for(n_sub * 32, 256), 256, 0, st>>>(rowptr, col, subset, n_sub, n, node_map, out_rowptr, out_col);
     SGF_LAUNCH_CHECK(); count_launch();
     subset_unmap_kernel<<<grid_for(n_sub, 256), 256, 0, st>>>(subset, n_sub, n, node_map);

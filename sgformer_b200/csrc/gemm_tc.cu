@@ -107,7 +107,7 @@ struct Params {
     float alpha, beta;
     const float* alpha_dev; const float* beta_dev;
     int relu, accumulate;
-    float nf; float* den_out;
+    float nf; const float* nf_dev; float* den_out;
     const float* r1_row; const float* r1_col;
     int tma_store;   // 1: epilogue stages 128-byte rows in smem and stores them with TMA; 0: direct global stores
     float* col_sum; float* col_sumsq;   // optional fused column statistics of the STORED output (tma_store path only)
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
         const bool f_rs = GEN ? p.row_scale != nullptr : (F & F_ROWSCALE) != 0;
         const bool f_acc = GEN ? p.accumulate != 0 : (F & F_ACCUM) != 0;
         const bool f_r1 = GEN ? p.r1_row != nullptr : (F & F_R1) != 0;
-        const bool f_attn = GEN ? p.epi == SGF_EPI_ATTN_APPLY : (F & F_ATTN) != 0;
+        const bool f_attn = GEN ? (p.epi == SGF_EPI_ATTN_APPLY || p.epi == SGF_EPI_ATTN_GRAM) : (F & F_ATTN) != 0;
         const bool f_tma = GEN ? p.tma_store != 0 : true;
         const bool f_stats = GEN ? want_stats : false;
         const int out_dtype = GEN ? p.out_dtype : 1;
@@ -412,12 +412,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
             float inv_den = 1.f;
+            const float nfv = (f_attn && p.nf_dev) ? *p.nf_dev : p.nf;
             if (f_attn) {
                 float t[16];
                 __syncwarp();
                 tmem_ld16(taddr + p.bn_main, t);
                 tmem_ld_wait();
-                const float den = t[0] + p.nf;
+                const float den = t[0] + nfv;
                 inv_den = 1.f / den;
                 if (row_ok && p.den_out && half == 0 && n_blk == 0) p.den_out[row] = den;
             }
@@ -455,20 +456,35 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                     const bool full32 = ncol == 32;
                     if (row_ok && ncol > 0) {
                         if (f_attn) {
-                            if (have_ad) {
+                            // out = (acc + nf*aux + bias) / (tail + nf): ATTN_APPLY carries aux (= v), ATTN_GRAM the bias bt
+                            if (f_aux) {
+                                if (have_ad) {
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    float a8[8];
-                                    Vec16<__nv_bfloat16>::unpack(cur[c], a8);
+                                    for (int c = 0; c < 4; ++c) {
+                                        float a8[8];
+                                        Vec16<__nv_bfloat16>::unpack(cur[c], a8);
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[8 * c + j] = (v[8 * c + j] + p.nf * a8[j]) * inv_den;
+                                        for (int j = 0; j < 8; ++j) v[8 * c + j] += nfv * a8[j];
+                                    }
+                                } else if constexpr (GEN) {
+                                    float ax[32];
+                                    load32(p.aux, p.aux_dtype, row * p.ld_aux + col0, full32 && aux_vec_ok, ncol, ax);
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] += nfv * ax[j];
                                 }
-                            } else if constexpr (GEN) {
-                                float ax[32];
-                                load32(p.aux, p.aux_dtype, row * p.ld_aux + col0, full32 && aux_vec_ok, ncol, ax);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = (v[j] + p.nf * ax[j]) * inv_den;
                             }
+                            if (f_bias) {
+                                if (!GEN || (full32 && vecf_ok && (col0 & 3) == 0)) {
+                                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { float4 b4 = __ldg(bp + j); v[4*j] += b4.x; v[4*j+1] += b4.y; v[4*j+2] += b4.z; v[4*j+3] += b4.w; }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += p.bias[col0 + j];
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= inv_den;
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] *= alpha;
@@ -776,6 +792,8 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     const bool has_tail = a->b_tail != nullptr;
     if (has_tail && (a->n_b != 1 || a->n_out > 256)) return SGF_ERR_ARG;
     if (a->epi == SGF_EPI_ATTN_APPLY && (!has_tail || !a->aux)) return SGF_ERR_ARG;
+    if (a->epi == SGF_EPI_ATTN_GRAM && (!has_tail || !a->bias || !a->nf_dev || a->aux)) return SGF_ERR_ARG;
+    if (a->epi != SGF_EPI_AFFINE && a->epi != SGF_EPI_ATTN_APPLY && a->epi != SGF_EPI_ATTN_GRAM) return SGF_ERR_ARG;
     if ((a->r1_row == nullptr) != (a->r1_col == nullptr)) return SGF_ERR_ARG;
 
     nt::Params p;
@@ -833,7 +851,7 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     p.row_scale = a->row_scale;
     p.alpha = a->alpha; p.beta = a->beta; p.alpha_dev = a->alpha_dev; p.beta_dev = a->beta_dev;
     p.relu = a->relu; p.accumulate = a->accumulate;
-    p.nf = a->nf; p.den_out = a->den_out;
+    p.nf = a->nf; p.nf_dev = a->nf_dev; p.den_out = a->den_out;
     p.r1_row = a->r1_row; p.r1_col = a->r1_col;
     {
         const int es = a->out_dtype == 1 ? 2 : 4;
@@ -864,7 +882,7 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     // epilogue specialisation: the exact feature set of this call if it has a compiled instantiation, else the generic kernel
     int feat = (a->bias ? nt::F_BIAS : 0) | (a->aux ? nt::F_AUX : 0) | (a->relu ? nt::F_RELU : 0) |
                (a->row_scale ? nt::F_ROWSCALE : 0) | (a->accumulate ? nt::F_ACCUM : 0) | (a->r1_row ? nt::F_R1 : 0) |
-               (a->epi == SGF_EPI_ATTN_APPLY ? nt::F_ATTN : 0);
+               (a->epi != SGF_EPI_AFFINE ? nt::F_ATTN : 0);
     const bool al16 = (!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
                       (!a->r1_col || (reinterpret_cast<uintptr_t>(a->r1_col) & 15) == 0) &&
                       (!a->aux || (a->aux_dtype == 1 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && (a->ld_aux * 2) % 16 == 0));
@@ -897,6 +915,9 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
             SGF_NT_CASE(nt::F_AUX | nt::F_BIAS)
             SGF_NT_CASE(nt::F_AUX | nt::F_R1)
             SGF_NT_CASE(nt::F_AUX | nt::F_ATTN)
+            SGF_NT_CASE(nt::F_BIAS | nt::F_ATTN)
+            SGF_NT_CASE(nt::F_BIAS | nt::F_R1)
+            SGF_NT_CASE(nt::F_BIAS | nt::F_R1 | nt::F_ACCUM)
             SGF_NT_CASE(nt::F_GENERIC)
             default: break;
         }

@@ -344,6 +344,124 @@ __global__ void __launch_bounds__(kRowBlock, 3) ln_bwd_kernel(const T* __restric
     if (use_ln && dbeta) flush_columns<T, CPL>(L, db, sm, h, dbeta);
 }
 
+// LayerNorm backward of y = dropout(relu?(LN?(a*o + b*r))) fused with the row prologue of the Gram-form attention backward
+// (engine.attention_gram_backward): with ga = a*du (gradient of the attention output o) and den~ = the forward's normalised
+// denominator,   gnum' = ga / den~,   gden' = -(ga . o) / den~,   dr = b*du,
+// and the column sums cs = sum_r gnum'[r,:], pg = sum_r xa[r,:]*gden'[r], sg = sum_r gden'[r] that the h x h backward algebra
+// needs (sgf_attn_gram_prepare_bwd) accumulate in registers like dgamma / dbeta.  xa = the attention layer's input (== r when
+// the layer has a residual connection: then it is not loaded twice).
+template <typename T, int CPL, bool DROP>
+__global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_kernel(const T* __restrict__ dy, const T* __restrict__ o, const T* __restrict__ rr,
+                                                                    const T* __restrict__ xa, int64_t ld, int64_t rows, int h, int chunks,
+                                                                    int lpr_log2, float a, float b, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, const float* __restrict__ stats,
+                                                                    int use_ln, int use_relu, float p, uint64_t seed, float gscale,
+                                                                    const float* __restrict__ den, T* __restrict__ gnum,
+                                                                    float* __restrict__ gden, T* __restrict__ dr,
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                    float* __restrict__ cs, float* __restrict__ pg, float* __restrict__ sg) {
+    constexpr int VN = Vec16<T>::N;
+    extern __shared__ float sm[];
+    Lane<T, CPL> L(chunks, lpr_log2);
+    float g[CPL][VN], be[CPL][VN], dg[CPL][VN], db[CPL][VN], acs[CPL][VN], apg[CPL][VN];
+    L.load_vec(use_ln ? gamma : nullptr, g, 1.f);
+    L.load_vec(use_ln ? beta : nullptr, be, 0.f);
+    SGF_ZERO(dg) SGF_ZERO(db) SGF_ZERO(acs) SGF_ZERO(apg)
+    float asg = 0.f;
+    const float inv_h = 1.f / (float)h;
+    const uint32_t thr16 = dropout_thr16(p);
+    const float inv_keep = dropout_inv_keep(thr16);
+    const bool xa_is_r = (xa == rr);
+    uint4 nx[CPL], nr[CPL], ng[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; ng[c] = nx[c]; }
+    float nmean = 0.f, nrstd = 1.f, ninv = 0.f;
+    if (L.row0 < rows) {
+        L.load_raw(o, ld, L.row0, nx);
+        if (rr) L.load_raw(rr, ld, L.row0, nr);
+        L.load_raw(dy, ld, L.row0, ng);
+        if (use_ln) { nmean = stats[2 * L.row0]; nrstd = stats[2 * L.row0 + 1]; }
+        ninv = 1.f / den[L.row0];
+    }
+#pragma unroll 1
+    for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
+        const int64_t r = rb + L.grp;
+        const bool live = r < rows;
+        float ov[CPL][VN], u[CPL][VN], gy[CPL][VN], t[CPL][VN];
+        const float mean = nmean, rstd = nrstd, inv_den = ninv;
+        L.unpack(nx, ov);
+        L.unpack(ng, gy);
+        if (rr) {
+            L.unpack(nr, t);
+            SGF_FOR_ELEMS u[c][i] = a * ov[c][i] + b * t[c][i];
+        } else {
+            SGF_FOR_ELEMS { u[c][i] = a * ov[c][i]; t[c][i] = 0.f; }
+        }
+        if (!xa_is_r) {
+            if (live) L.load(xa, ld, r, t);
+            else SGF_ZERO(t)
+        }
+        {
+            const int64_t rn = r + L.row_step;
+            if (rn < rows) {
+                L.load_raw(o, ld, rn, nx);
+                if (rr) L.load_raw(rr, ld, rn, nr);
+                L.load_raw(dy, ld, rn, ng);
+                if (use_ln) { nmean = stats[2 * rn]; nrstd = stats[2 * rn + 1]; }
+                ninv = 1.f / den[rn];
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) { nx[c] = make_uint4(0u, 0u, 0u, 0u); nr[c] = nx[c]; ng[c] = nx[c]; }
+                nmean = 0.f; nrstd = 1.f; ninv = 0.f;
+            }
+        }
+        SGF_FOR_ELEMS gy[c][i] *= gscale;
+        if (DROP) L.dropout(gy, seed, r, chunks, thr16, inv_keep);
+        float du[CPL][VN];
+        if (use_ln) {
+            float s1 = 0.f, s2 = 0.f;
+            SGF_FOR_ELEMS {
+                float xh = L.cval[c] ? (u[c][i] - mean) * rstd : 0.f;
+                float pre = xh * g[c][i] + be[c][i];
+                float gg = (use_relu && pre <= 0.f) ? 0.f : gy[c][i];
+                dg[c][i] += gg * xh;
+                db[c][i] += gg;
+                gg *= g[c][i];
+                u[c][i] = xh;
+                gy[c][i] = gg;
+                s1 += gg;
+                s2 += gg * xh;
+            }
+            s1 = L.row_sum(s1) * inv_h;
+            s2 = L.row_sum(s2) * inv_h;
+            SGF_FOR_ELEMS du[c][i] = rstd * (gy[c][i] - s1 - u[c][i] * s2);
+        } else {
+            SGF_FOR_ELEMS du[c][i] = (use_relu && u[c][i] <= 0.f) ? 0.f : gy[c][i];
+        }
+        // attention-backward prologue on ga = a*du
+        float dot = 0.f;
+        SGF_FOR_ELEMS { const float ga = L.cval[c] ? a * du[c][i] : 0.f; dot += ga * ov[c][i]; gy[c][i] = ga * inv_den; }
+        dot = L.row_sum(dot);
+        const float gd = live ? -dot * inv_den : 0.f;
+        SGF_FOR_ELEMS { acs[c][i] += gy[c][i]; apg[c][i] += t[c][i] * gd; }
+        if (L.sub == 0) asg += gd;
+        if (live) {
+            L.store(gnum, ld, r, gy);
+            if (L.sub == 0) gden[r] = gd;
+            if (dr) {
+                SGF_FOR_ELEMS gy[c][i] = b * du[c][i];
+                L.store(dr, ld, r, gy);
+            }
+        }
+    }
+    if (use_ln && dgamma) flush_columns<T, CPL>(L, dg, sm, h, dgamma);
+    if (use_ln && dbeta) flush_columns<T, CPL>(L, db, sm, h, dbeta);
+    flush_columns<T, CPL>(L, acs, sm, h, cs);
+    flush_columns<T, CPL>(L, apg, sm, h, pg);
+    asg = warp_sum(asg);
+    if (L.lane == 0 && asg != 0.f) atomicAdd(sg, asg);
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm family (column statistics supplied)
 __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int64_t rows, int h, float eps,
@@ -956,6 +1074,26 @@ extern "C" int sgf_ln_bwd(const void* dy, const void* x, const void* r, int64_t 
     SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                          (const T*)dy, (const T*)x, (const T*)r, ld, rows, h, g.chunks, g.lpr_log2, a, b, gamma, beta,
                                          stats, use_ln, use_relu, p, seed, gscale, (T*)dx, (T*)dr, dgamma, dbeta)));
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, const void* xa, int64_t ld, int64_t rows, int h,
+                               int dtype, float a, float b, const float* gamma, const float* beta, const float* stats, int use_ln,
+                               int use_relu, float p, uint64_t seed, float gscale, const float* den, void* gnum, float* gden,
+                               void* dr, float* dgamma, float* dbeta, float* cs, float* pg, float* sg, void* stream) {
+    RowGeom g;
+    if (!geom_for(dtype, h, g) || !aligned16(o) || !aligned16(dy) || !aligned16(gnum) || !aligned16(r) || !aligned16(dr) ||
+        !aligned16(xa) || !ld_ok(dtype, ld) || rows < 0)
+        return SGF_ERR_ARG;
+    if (!o || !dy || !xa || !den || !gnum || !gden || !cs || !pg || !sg) return SGF_ERR_ARG;
+    if (use_ln && (!gamma || !beta || !stats)) return SGF_ERR_ARG;
+    if (rows == 0) return SGF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                         (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,
+                                         gamma, beta, stats, use_ln, use_relu, p, seed, gscale, den, (T*)gnum, gden, (T*)dr, dgamma,
+                                         dbeta, cs, pg, sg)));
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

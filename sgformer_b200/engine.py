@@ -13,6 +13,7 @@ medium/models.py:49-63 (GCN over PyG GCNConv), large/ours.py:265-276 (SGFormer.f
 from __future__ import annotations
 
 import itertools
+import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -20,7 +21,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import kernels as K
-from ._lib import EPI_ATTN_APPLY
+from ._lib import EPI_ATTN_APPLY, EPI_ATTN_GRAM
 from .dist import SINGLE, Comm
 from .graph import Graph
 
@@ -60,6 +61,15 @@ _seed_counter = itertools.count(1)
 def next_seed() -> int:
     """Per-forward dropout seed: deterministic under torch.manual_seed, no device sync."""
     return ((torch.initial_seed() * 0x9E3779B1) ^ (next(_seed_counter) * 0x85EBCA6B)) & 0x7FFFFFFFFFFFFFFF
+
+
+def check_width(h: int, prec: Precision, what: str):
+    """The row kernels move rows in 16-byte chunks, at most 128 chunks per row (csrc/rowops.cu make_geom): fail with a clear
+    message instead of SGF_ERR_ARG from the first LayerNorm/BatchNorm launch.  (The reference has no such limit.)"""
+    vn = 8 if prec.name == "bf16" else 4
+    if h % vn != 0 or h > 128 * vn:
+        raise ValueError(f"sgformer_b200: {what} = {h} is not supported in precision '{prec.name}': it must be a multiple of {vn} "
+                         f"and at most {128 * vn}" + (" (use set_precision('bf16') for wider layers)" if prec.name != "bf16" and h % 8 == 0 and h <= 1024 else ""))
 
 
 class Tape(dict):
@@ -172,6 +182,80 @@ def attention_backward(tape: Tape, g: Tensor, gscale: float, prec: Precision, dq
 
 
 # =================================================================================================
+# linear attention in Gram form (single head): projections + full_attention_conv without materialising q, k, v
+# =================================================================================================
+# With q = x Wq^T + bq, k = x Wk^T + bk, v = x Wv^T + bv every node-contracted quantity of full_attention_conv
+# (medium/ours.py:16-31) is a function of the Gram matrix G = x^T x and the column sums s = x^T 1 of the layer input:
+#   k^T v = Wk G Wv^T + (Wk s) bv^T + bk (Wv s)^T + N bk bv^T,   k^T 1 = Wk s + N bk,
+#   ||k||^2 = <Wk G + bk s^T, Wk> + (k^T 1).bk   (same for q),
+# so pass 1 is ONE node contraction x^T x (reads x once) and pass 2 ONE GEMM x . Bt^T with
+#   Bt = (alpha/N) S'^T Wq + Wv,  out = (x Bt^T + bt) / (x ct + dt)      (alpha = 1/(||q|| ||k||); see sgf_attn_gram_prepare_fwd).
+# The backward contracts P = x^T gnum', x^T gden' the same way: dWq, dWk, dWv come out of h x h algebra, dx is one
+# two-segment GEMM [gnum' | x] . [Bt | A3] (sgf_attn_gram_prepare_bwd).  Forward traffic 3 N h b instead of 12 N h b,
+# 4 N h^2 flops instead of 10 N h^2; identical mathematics (fp64 check: tests/test_gram_attention_math.py).
+GRAM_ATTENTION = os.environ.get("SGF_GRAM_ATTENTION", "1") == "1"
+
+_eye_cache: dict = {}
+
+
+def _identity_v(h: int, dev):
+    """use_weight=False: V is the layer input itself (medium/ours.py:84) = projection by the identity with zero bias."""
+    key = (h, str(dev))
+    if key not in _eye_cache:
+        _eye_cache[key] = (torch.eye(h, dtype=torch.float32, device=dev), torch.zeros(h, dtype=torch.float32, device=dev))
+    return _eye_cache[key]
+
+
+def attention_gram_forward(P: Dict[str, Tensor], lp: str, x: Tensor, use_weight: bool, prec: Precision, tape: Optional[Tape],
+                           comm: Comm = SINGLE) -> Tensor:
+    """x: [N, h] layer input (activation) -> full_attention_conv(Wq x, Wk x, Wv x) [N, h], one head."""
+    n_loc, h = x.shape
+    n = comm.n_global if comm.active else n_loc
+    dev = x.device
+    xop = K.as_operand(x, prec.planes, memo=True)
+    G, s = K.gram(xop, x)
+    comm.allreduce_(G, s)                                     # C1: h*h + h floats
+    wv, bv = (P[lp + "Wv.weight"], P[lp + "Wv.bias"]) if use_weight else _identity_v(h, dev)
+    st = K.attn_gram_prepare_fwd(G, s, P[lp + "Wq.weight"], P[lp + "Wq.bias"], P[lp + "Wk.weight"], P[lp + "Wk.bias"], wv, bv, n)
+    bop = K.pack_operand(st.Bt, False, prec.planes)
+    btail = K.pack_operand(st.tail, False, prec.planes)
+    d = st.Bt.shape[0]
+    o = K.alloc_act(n_loc, d, x.dtype, dev)
+    den = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    K.gemm_nt([xop], [bop], [(0, 0, 0, 0, h)], d, o, epi=EPI_ATTN_GRAM, bias=st.bt, tail=btail,
+              nf_dev=st.sc[K.SC_DEN:K.SC_DEN + 1], den_out=den)
+    if tape is not None:
+        tape.update(st=st, den=den, xop=xop, n=n)
+    return o
+
+
+def attention_gram_backward(P: Dict[str, Tensor], lp: str, tape: Tape, x: Tensor, gnum: Tensor, gden: Tensor, cs: Tensor,
+                            pg: Tensor, sg: Tensor, use_weight: bool, prec: Precision, dprev: Tensor, accumulate: bool,
+                            grads: Dict[str, Tensor], comm: Comm = SINGLE):
+    """gnum' = g/den~ [N,h], gden' = -(g.o)/den~ [N] and their column sums (sgf_ln_bwd_attn) -> parameter gradients and
+    dprev (+)= d/dx of the attention (through q, k and v)."""
+    st = tape["st"]
+    h = x.shape[1]
+    d = gnum.shape[1]
+    dev = x.device
+    gnum_op = K.as_operand(gnum, prec.planes)
+    pmat = torch.empty((h, d), dtype=torch.float32, device=dev)
+    K.gemm_tn(tape["xop"], gnum_op, pmat)
+    comm.allreduce_(pmat, pg, cs, sg)                         # C2
+    dwq, dbq, dwk, dbk, dwv, dbv, bcat, a4 = K.attn_gram_prepare_bwd(st, pmat, pg, cs, sg)
+    grads[lp + "Wq.weight"], grads[lp + "Wq.bias"] = dwq, dbq
+    grads[lp + "Wk.weight"], grads[lp + "Wk.bias"] = dwk, dbk
+    names = [lp + "Wq.weight", lp + "Wq.bias", lp + "Wk.weight", lp + "Wk.bias"]
+    if use_weight:
+        grads[lp + "Wv.weight"], grads[lp + "Wv.bias"] = dwv, dbv
+        names += [lp + "Wv.weight", lp + "Wv.bias"]
+    _mark_global(grads, comm, *names)          # built from all-reduced contractions: already global sums
+    bop = K.pack_operand(bcat, False, prec.planes)
+    K.gemm_nt([gnum_op, tape["xop"]], [bop], [(0, 0, 0, 0, d), (1, 0, 0, d, h)], h, dprev, bias=a4, r1_row=gden,
+              r1_col=st.tail[0], accumulate=accumulate)
+
+
+# =================================================================================================
 # TransConv branch
 # =================================================================================================
 def _res_coef(cfg: dict):
@@ -192,6 +276,7 @@ def _qkv_weight(P, pfx: str, use_weight: bool) -> (Tensor, Tensor):
 def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precision, training: bool, seed: int,
                   tape: Optional[Tape], pfx: str = "trans_conv.", comm: Comm = SINGLE) -> Tensor:
     h, H, d_in = cfg["hidden"], cfg["num_heads"], cfg["in_channels"]
+    check_width(h, prec, "hidden_channels")
     n = xin.rows
     dev = xin.data.device
     p = float(cfg["trans_dropout"]) if training else 0.0
@@ -208,6 +293,15 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
         raise ValueError("use_weight=False requires num_heads == 1 (medium/ours.py:84)")
     for i in range(cfg["trans_num_layers"]):
         lp = f"{pfx}convs.{i}."
+        if GRAM_ATTENTION and H == 1:
+            at = Tape() if tape is not None else None
+            a = attention_gram_forward(P, lp, x, use_weight, prec, at, comm)
+            y, st = K.ln_fwd(a, x if use_res else None, ca, cb, P.get(f"{pfx}bns.{i + 1}.weight"), P.get(f"{pfx}bns.{i + 1}.bias"),
+                             use_ln, bool(cfg["trans_use_act"]), p, seed + 211 + i, tape is not None)
+            if tape is not None:
+                tape["layers"].append(dict(x_in=x, attn=at, a=a, st=st, gram=True))
+            x = y
+            continue
         wcat, bcat = _qkv_weight(P, lp, use_weight)
         nout = wcat.shape[0]
         qkv = torch.empty((n, K.ceil_to(nout, 8)), dtype=prec.act_dtype, device=dev)[:, :nout]
@@ -244,8 +338,20 @@ def trans_backward(P, cfg: dict, tape: Tape, dout: Tensor, gscale: float, prec: 
     for i in reversed(range(cfg["trans_num_layers"])):
         L = tape["layers"][i]
         lp = f"{pfx}convs.{i}."
-        x_in, qkv, at, nout = L["x_in"], L["qkv"], L["attn"], L["nout"]
         dg, db = (zeros(h), zeros(h)) if use_ln else (None, None)
+        if L.get("gram"):
+            x_in, at = L["x_in"], L["attn"]
+            gnum, gden, dr, cs, pg, sg = K.ln_bwd_attn(dcur, L["a"], x_in if use_res else None, x_in, ca, cb,
+                                                       P.get(f"{pfx}bns.{i + 1}.weight"), P.get(f"{pfx}bns.{i + 1}.bias"), L["st"],
+                                                       use_ln, bool(cfg["trans_use_act"]), p, seed + 211 + i, gs, use_res, dg, db,
+                                                       at["den"])
+            if use_ln:
+                grads[f"{pfx}bns.{i + 1}.weight"], grads[f"{pfx}bns.{i + 1}.bias"] = dg, db
+            dprev = dr if dr is not None else K.new_like(x_in)
+            attention_gram_backward(P, lp, at, x_in, gnum, gden, cs, pg, sg, use_weight, prec, dprev, dr is not None, grads, comm)
+            dcur, gs = dprev, 1.0
+            continue
+        x_in, qkv, at, nout = L["x_in"], L["qkv"], L["attn"], L["nout"]
         da, dr = K.ln_bwd(dcur, L["a"], x_in if use_res else None, ca, cb, P.get(f"{pfx}bns.{i + 1}.weight"),
                           P.get(f"{pfx}bns.{i + 1}.bias"), L["st"], use_ln, bool(cfg["trans_use_act"]), p, seed + 211 + i, gs,
                           use_res, dg, db)
@@ -342,6 +448,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     """Returns GraphConv(x) — or, when `mix` is given, gw*GraphConv(x) + (1-gw)*mix (the SGFormer branch sum fused
     into the last layer's epilogue pass)."""
     h, d_in, nl = cfg["hidden"], cfg["in_channels"], cfg["gnn_num_layers"]
+    check_width(h, prec, "hidden_channels")
     n = xin.rows
     dev = xin.data.device
     p = float(cfg["gnn_dropout"]) if training else 0.0
@@ -510,6 +617,7 @@ def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, tra
         last = i == nl - 1
         wname = f"{pfx}convs.{i}.lin.weight"
         hout = P[wname].shape[0]
+        check_width(hout, prec, f"GCN layer {i} out_channels")
         t = K.gemm_nt([cur_op], [_w(P, wname, prec)], [(0, 0, 0, 0, cur_k)], hout, K.alloc_act(n, hout, prec.act_dtype, dev),
                       row_scale=dinv)
         s = comm.spmm_gathered(K.spmm, graph.rowptr, graph.col, dinv, t, heavy=graph.heavy)

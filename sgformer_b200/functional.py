@@ -5,6 +5,7 @@ the others back the standalone modules/functions of the reference surface (Trans
 full_attention_conv, GraphConvLayer's SpMM, nn.Linear on the tensor-core GEMM)."""
 from __future__ import annotations
 
+import threading
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -16,6 +17,26 @@ from .dist import SINGLE, Comm
 from .graph import Graph
 
 Tensor = torch.Tensor
+
+_outer = threading.local()
+
+
+def _want_tape(ctx) -> bool:
+    """Whether the forward must record its tape: some input requires grad AND the caller is not under torch.no_grad()
+    (`needs_input_grad` ignores the grad mode, and inside Function.forward grad mode is always off: the caller's mode is sampled
+    by `_TapeFunction.apply`).  Eval forwards (evaluate() is @torch.no_grad, large/eval.py) then keep no activations alive."""
+    return getattr(_outer, "grad_enabled", True) and any(ctx.needs_input_grad)
+
+
+class _TapeFunction(Function):
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        prev = getattr(_outer, "grad_enabled", True)
+        _outer.grad_enabled = torch.is_grad_enabled()
+        try:
+            return super().apply(*args, **kwargs)
+        finally:
+            _outer.grad_enabled = prev
 
 
 def _pdict(names: Sequence[str], tensors: Sequence[Tensor]) -> Dict[str, Tensor]:
@@ -57,7 +78,7 @@ def _from_act(t: Tensor, dtype) -> Tensor:
     return t.to(dtype)
 
 
-class SGFormerFn(Function):
+class SGFormerFn(_TapeFunction):
     """Fused encoder: logits = fc(mix(TransConv(x), GNN(x, graph))).  Returns fp32 [N, c]."""
 
     @staticmethod
@@ -65,10 +86,12 @@ class SGFormerFn(Function):
                 *params):
         """x: the rows this rank owns ([N, d_in], or its [N/P, d_in] block when `comm` is a row-sharding Comm)."""
         P = _pdict(names, params)
-        need_tape = any(ctx.needs_input_grad)
+        need_tape = _want_tape(ctx)
         K.operand_memo_begin()       # fp32 activations shared by several GEMMs of this step are packed once
         xin = E.input_operand(x, prec)
         seed = E.next_seed()
+        if comm.active:     # row shards hash local row ids: decorrelate the shards' dropout masks
+            seed = (seed + comm.rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         tt, tg, th = (E.Tape(), E.Tape(), E.Tape()) if need_tape else (None, None, None)
         x1 = E.trans_forward(P, cfg, xin, prec, training, seed, tt, comm=comm)
         gw = float(cfg["graph_weight"])
@@ -116,13 +139,13 @@ class SGFormerFn(Function):
         return (dx, None, None, None, None, None, None, *_grad_list(names, params, grads))
 
 
-class TransConvFn(Function):
+class TransConvFn(_TapeFunction):
     """Standalone TransConv branch.  Returns [N, h] in x's dtype."""
 
     @staticmethod
     def forward(ctx, x, cfg, prec, training, names, *params):
         P = _pdict(names, params)
-        need_tape = any(ctx.needs_input_grad)
+        need_tape = _want_tape(ctx)
         tape = E.Tape() if need_tape else None
         out = E.trans_forward(P, cfg, E.input_operand(x, prec), prec, training, E.next_seed(), tape)
         if need_tape:
@@ -138,13 +161,13 @@ class TransConvFn(Function):
         return (dx, None, None, None, None, *_grad_list(names, params, grads))
 
 
-class GraphBranchFn(Function):
+class GraphBranchFn(_TapeFunction):
     """Standalone GNN branch: GraphConv (large/100M) or the PyG-GCN backbone (medium).  Returns [N, h] in x's dtype."""
 
     @staticmethod
     def forward(ctx, x, graph, cfg, prec, training, kind, pfx, names, *params):
         P = _pdict(names, params)
-        need_tape = any(ctx.needs_input_grad)
+        need_tape = _want_tape(ctx)
         tape = E.Tape() if need_tape else None
         fwd = E.gcn_forward if kind == "gcn" else E.gconv_forward
         out = fwd(P, cfg, E.input_operand(x, prec), graph, prec, training, E.next_seed(), tape, pfx=pfx)
@@ -197,7 +220,7 @@ class HeadFn(Function):
         return (d1, d2, None, None, None, *_grad_list(names, params, grads))
 
 
-class AttentionFn(Function):
+class AttentionFn(_TapeFunction):
     """full_attention_conv(qs, ks, vs) -> [N, H, D]  (medium/ours.py:14-34, 100M/ours.py:12-43)."""
 
     @staticmethod
@@ -205,7 +228,7 @@ class AttentionFn(Function):
         n, heads, m = q.shape
         d = v.shape[2]
         qa, ka, va = (_to_act(t.reshape(n, -1), prec) for t in (q, k, v))
-        need = any(ctx.needs_input_grad)
+        need = _want_tape(ctx)
         tape = E.Tape() if need else None
         o = E.attention_forward(qa, ka, va, heads, prec, tape)
         if need:

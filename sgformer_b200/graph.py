@@ -69,8 +69,10 @@ class Graph:
             self._symmetric = self.transpose()[0] is self.rowptr
             if not self._symmetric:
                 raise NotImplementedError("Graph.subset: directed graphs need the transposed subset as well")
-        rp, cl, dv = K.csr_subset(self.rowptr, self.col, self.n, idx, self._node_map, capacity)
-        return Graph._from_parts(idx.numel(), rp, cl, dv, True)
+        rp, cl, dv, needed = K.csr_subset(self.rowptr, self.col, self.n, idx, self._node_map, capacity)
+        g = Graph._from_parts(idx.numel(), rp, cl, dv, True)
+        g.nnz_needed, g.capacity = needed, capacity      # device int64 [1]: > capacity means the batch structure was truncated
+        return g
 
     def transpose(self) -> Tuple[Tensor, Tensor]:
         """CSR of the transposed pattern (rows = edge sources) for the backward SpMM; shares storage when the edge

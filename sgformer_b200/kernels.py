@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_AFFINE, EPI_ATTN_APPLY, F32, GemmNtArgs, GemmTnArgs, check
+from ._lib import BF16, EPI_AFFINE, EPI_ATTN_APPLY, EPI_ATTN_GRAM, F32, AttnGramArgs, GemmNtArgs, GemmTnArgs, check
 
 Tensor = torch.Tensor
 _tls = threading.local()
@@ -182,8 +182,10 @@ spmm_events = None
 
 
 def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Tensor, capacity: Optional[int] = None):
-    """Induced-subgraph CSR of `subset` from the full CSR.  -> (rowptr int64 [b+1], col int32 [nnz_b], dinv fp32 [b]).
-    `capacity` bounds the output nnz (default: a device sync to read the exact sum of the subset rows' lengths)."""
+    """Induced-subgraph CSR of `subset` from the full CSR.  -> (rowptr int64 [b+1], col int32 [nnz_b], dinv fp32 [b], needed).
+    `capacity` bounds the output nnz (default: a device sync to read the exact sum of the subset rows' lengths); the kernels
+    never write past it, and `needed` (device int64 [1]) holds the nnz the untruncated result requires: needed > capacity
+    means the batch was truncated (checked without a per-batch sync by RandomPartitionSampler.check)."""
     _use(rowptr)
     subset = subset.contiguous().to(torch.int64)
     b = subset.numel()
@@ -194,14 +196,15 @@ def csr_subset(rowptr: Tensor, col: Tensor, n: int, subset: Tensor, node_map: Te
     out_rowptr = torch.empty(b + 1, dtype=torch.int64, device=dev)
     out_col = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
     dinv = torch.empty(max(b, 1), dtype=torch.float32, device=dev)
+    needed = torch.empty(1, dtype=torch.int64, device=dev)
     nbytes = C.c_size_t(0)
     check(lib().sgf_csr_subset_ws_bytes(b, capacity, C.byref(nbytes)), "sgf_csr_subset_ws_bytes")
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
     check(lib().sgf_csr_subset(_p(rowptr), _p(col), n, _p(subset), b, _p(node_map), _p(out_rowptr), _p(out_col), capacity,
-                               _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_subset")
+                               _p(dinv), _p(needed), _p(ws), nbytes.value, _stream()), "sgf_csr_subset")
     if trim:    # exact-size result (one more device sync); with a caller-provided capacity the tail of `col` is unused
         out_col = out_col[:int(out_rowptr[b].item())]
-    return out_rowptr, out_col, dinv[:b]
+    return out_rowptr, out_col, dinv[:b], needed
 
 
 HEAVY_ROW = 1024      # rows longer than this are processed in segments of HEAVY_ROW entries (hub rows of power-law graphs)
@@ -353,7 +356,7 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
             alpha_dev: Optional[Tensor] = None, beta_dev: Optional[Tensor] = None, relu: bool = False,
             accumulate: bool = False, tail: Optional[Operand] = None, nf: float = 0.0, den_out: Optional[Tensor] = None,
             r1_row: Optional[Tensor] = None, r1_col: Optional[Tensor] = None, col_sum: Optional[Tensor] = None,
-            col_sumsq: Optional[Tensor] = None, schedule: Optional[int] = None) -> Tensor:
+            col_sumsq: Optional[Tensor] = None, schedule: Optional[int] = None, nf_dev: Optional[Tensor] = None) -> Tensor:
     """out[rows, n_out] = epilogue(sum over `pairs` (ai, a_k0, bi, b_k0, klen) of A[ai][:, a_k0:+klen] . B[bi][:, b_k0:+klen]^T).
 
     Logical K offsets; 3-plane operands expand every pair into the six bf16x3 partial products."""
@@ -405,6 +408,7 @@ def gemm_nt(A: Sequence[Operand], B: Sequence[Operand], pairs: Sequence[Tuple[in
     args.alpha_dev, args.beta_dev = _p(alpha_dev), _p(beta_dev)
     args.relu, args.accumulate = int(relu), int(accumulate)
     args.nf, args.den_out = nf, _p(_f32vec(den_out, rows, "den_out"))
+    args.nf_dev = _p(_f32vec(nf_dev, 1, "nf_dev"))
     args.r1_row, args.r1_col = _p(_f32vec(r1_row, rows, "r1_row")), _p(_f32vec(r1_col, n_out, "r1_col"))
     fused_stats = (col_sum is not None or col_sumsq is not None) and stats_fusable(out)
     if fused_stats:
@@ -521,6 +525,26 @@ def ln_bwd(dy: Tensor, x: Tensor, r: Optional[Tensor], a: float, b: float, gamma
     check(lib().sgf_ln_bwd(_p(dy), _p(x), _p(r), ld, rows, h, dcode(x), a, b, _p(gamma), _p(beta), _p(stats), int(use_ln),
                            int(use_relu), p, seed, gscale, _p(dx), _p(dr), _p(dgamma), _p(dbeta), _stream()), "sgf_ln_bwd")
     return dx, dr
+
+
+def ln_bwd_attn(dy: Tensor, o: Tensor, r: Optional[Tensor], xa: Tensor, a: float, b: float, gamma, beta, stats, use_ln: bool,
+                use_relu: bool, p: float, seed: int, gscale: float, want_dr: bool, dgamma: Optional[Tensor],
+                dbeta: Optional[Tensor], den: Tensor):
+    """LayerNorm backward of y = dropout(relu?(LN?(a*o + b*r))) fused with the row prologue of the Gram-form attention
+    backward (sgf_ln_bwd_attn).  -> (gnum' [rows,h], gden' fp32 [rows], dr | None, cs [h], pg [h], sg [1])."""
+    _use(o)
+    rows, h, ld = _mat(o, "o")
+    gnum = new_like(o)
+    dr = new_like(o) if want_dr else None
+    _same_ld(ld, dy, r, xa, gnum, dr)
+    dev = o.device
+    gden = torch.empty(rows, dtype=torch.float32, device=dev)
+    acc = torch.zeros(2 * h + 1, dtype=torch.float32, device=dev)
+    cs, pg, sg = acc[:h], acc[h:2 * h], acc[2 * h:]
+    check(lib().sgf_ln_bwd_attn(_p(dy), _p(o), _p(r), _p(xa), ld, rows, h, dcode(o), a, b, _p(gamma), _p(beta), _p(stats),
+                                int(use_ln), int(use_relu), p, seed, gscale, _p(_f32vec(den, rows, "den")), _p(gnum), _p(gden),
+                                _p(dr), _p(dgamma), _p(dbeta), _p(cs), _p(pg), _p(sg), _stream()), "sgf_ln_bwd_attn")
+    return gnum, gden, dr, cs, pg, sg
 
 
 def bn_finalize(sum_: Optional[Tensor], sumsq: Optional[Tensor], rows: int, h: int, zbias: Optional[Tensor],
@@ -660,6 +684,101 @@ def attn_combine_scal(scal_bwd_all: Tensor, heads: int, scal_fwd: Tensor):
     _use(scal_bwd_all)
     check(lib().sgf_attn_combine_scal(_p(scal_bwd_all), heads, scal_bwd_all.stride(0), _p(scal_fwd), _stream()),
           "sgf_attn_combine_scal")
+
+
+# ------------------------------------------------------------------------------------------------
+# Gram-form linear attention (engine.attention_gram_forward / _backward)
+# ------------------------------------------------------------------------------------------------
+# slots of the device scalar vector `sc` (include/sgformer_b200.h: sgf_attn_gram_args.sc)
+SC_NQ2, SC_NK2, SC_ALPHA, SC_BETA, SC_DEN, SC_N, SC_IP, SC_C, SC_CQ, SC_CK, SC_SG = 0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12
+
+
+def gram(xop: Operand, x: Tensor):
+    """Pass 1 of the Gram-form attention: G = x^T x (fp32 [h,h]) and s = x^T 1 (fp32 [h]) of the layer input."""
+    h = xop.k
+    G = torch.empty((h, h), dtype=torch.float32, device=x.device)
+    gemm_tn(xop, xop, G)
+    s, _ = colstats(x, want_sumsq=False)
+    return G, s
+
+
+class GramState:
+    """fp32 device tensors written by sgf_attn_gram_prepare_fwd and re-read by its backward (h x h algebra on the weights)."""
+    __slots__ = ("wq", "bq", "wk", "bk", "wv", "bv", "G", "s", "kx", "qx", "vx", "z1", "q1", "v1", "S", "Bt", "tail", "bt", "sc",
+                 "n", "h", "m", "d", "ws")
+
+
+def _w2(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected an fp32 row-major matrix")
+    return t
+
+
+def _gram_args(st: GramState) -> AttnGramArgs:
+    a = AttnGramArgs()
+    a.h, a.m, a.d, a.n_nodes = st.h, st.m, st.d, st.n
+    a.wq, a.bq, a.wk, a.bk, a.wv, a.bv = (_p(t) for t in (st.wq, st.bq, st.wk, st.bk, st.wv, st.bv))
+    a.ld_wq, a.ld_wk, a.ld_wv = st.wq.stride(0), st.wk.stride(0), st.wv.stride(0)
+    a.G, a.s = _p(st.G), _p(st.s)
+    for f in ("kx", "qx", "vx", "z1", "q1", "v1", "S", "Bt", "tail", "bt", "sc"):
+        setattr(a, f, _p(getattr(st, f)))
+    a.ws, a.ws_floats = _p(st.ws), st.ws.numel()
+    return a
+
+
+def attn_gram_prepare_fwd(G: Tensor, s: Tensor, wq: Tensor, bq: Tensor, wk: Tensor, bk: Tensor, wv: Tensor, bv: Tensor,
+                          n: int) -> GramState:
+    """h x h algebra between the two passes (sgf_attn_gram_prepare_fwd): from G = x^T x, s = x^T 1 and the projection weights
+    -> Bt [d,h], tail [16,h] (row 0 = ct), bt [d], sc[SC_DEN] such that out = (x Bt^T + bt)/(x ct + sc[SC_DEN])."""
+    _use(G)
+    st = GramState()
+    st.wq, st.wk, st.wv = _w2(wq, "Wq"), _w2(wk, "Wk"), _w2(wv, "Wv")
+    st.bq, st.bk, st.bv = (t.contiguous() for t in (bq, bk, bv))
+    st.m, st.h = wq.shape
+    st.d = wv.shape[0]
+    st.n = int(n)
+    if wk.shape != wq.shape or wv.shape[1] != st.h or tuple(G.shape) != (st.h, st.h) or not G.is_contiguous():
+        raise ValueError("attn_gram_prepare_fwd: shape mismatch")
+    st.G, st.s = G, s
+    dev = G.device
+    h, m, d = st.h, st.m, st.d
+    # one allocation for the saved fp32 state
+    sizes = dict(kx=m * h, qx=m * h, vx=d * h, z1=m, q1=m, v1=d, S=m * d, Bt=d * h, tail=16 * h, bt=d, sc=16)
+    buf = torch.zeros(sum(ceil_to(v, 4) for v in sizes.values()), dtype=torch.float32, device=dev)
+    o = 0
+    shapes = dict(kx=(m, h), qx=(m, h), vx=(d, h), S=(m, d), Bt=(d, h), tail=(16, h))
+    for k_, v in sizes.items():
+        t = buf[o:o + v]
+        setattr(st, k_, t.view(shapes[k_]) if k_ in shapes else t)
+        o += ceil_to(v, 4)
+    nws = C.c_int64(0)
+    check(lib().sgf_attn_gram_ws_floats(h, m, d, C.byref(nws)), "sgf_attn_gram_ws_floats")
+    st.ws = torch.empty(max(nws.value, 1), dtype=torch.float32, device=dev)
+    check(lib().sgf_attn_gram_prepare_fwd(C.byref(_gram_args(st)), _stream()), "sgf_attn_gram_prepare_fwd")
+    return st
+
+
+def attn_gram_prepare_bwd(st: GramState, P: Tensor, pg: Tensor, cs: Tensor, sg: Tensor):
+    """-> (dWq, dbq, dWk, dbk, dWv, dbv, bcat fp32 [h, d+h], a4 fp32 [h]); see sgf_attn_gram_prepare_bwd."""
+    _use(P)
+    h, m, d = st.h, st.m, st.d
+    dev = P.device
+    if tuple(P.shape) != (h, d) or not P.is_contiguous():
+        raise ValueError("attn_gram_prepare_bwd: P must be contiguous fp32 [h, d]")
+    sizes = dict(dwq=m * h, dbq=m, dwk=m * h, dbk=m, dwv=d * h, dbv=d, bcat=h * (d + h), a4=h)
+    buf = torch.empty(sum(ceil_to(v, 4) for v in sizes.values()), dtype=torch.float32, device=dev)
+    out, o = {}, 0
+    shapes = dict(dwq=(m, h), dwk=(m, h), dwv=(d, h), bcat=(h, d + h))
+    for k_, v in sizes.items():
+        t = buf[o:o + v]
+        out[k_] = t.view(shapes[k_]) if k_ in shapes else t
+        o += ceil_to(v, 4)
+    a = _gram_args(st)
+    a.P, a.pg, a.cs, a.sg = _p(P), _p(_f32vec(pg, h, "pg")), _p(_f32vec(cs, d, "cs")), _p(_f32vec(sg, 1, "sg"))
+    for k_ in sizes:
+        setattr(a, k_, _p(out[k_]))
+    check(lib().sgf_attn_gram_prepare_bwd(C.byref(a), _stream()), "sgf_attn_gram_prepare_bwd")
+    return out["dwq"], out["dbq"], out["dwk"], out["dbk"], out["dwv"], out["dbv"], out["bcat"], out["a4"]
 
 
 def softmax_nll(logits: Tensor, labels: Tensor, mask: Optional[Tensor], scale: float, want_grad: bool = True):

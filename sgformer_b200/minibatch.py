@@ -33,15 +33,26 @@ class RandomPartitionSampler:
         self.graph, self.x, self.y, self.batch_size = graph, x, y, int(batch_size)
         self.capacity, self.generator = capacity, generator
         self.n = graph.n
+        self._max_needed = None      # device int64 [1]: largest induced nnz any batch needed (overflow check without per-batch syncs)
 
     def __len__(self) -> int:
         return (self.n + self.batch_size - 1) // self.batch_size
 
     def batch(self, idx: Tensor) -> MiniBatch:
         g = self.graph.subset(idx, self.capacity)
+        if self.capacity is not None:
+            self._max_needed = g.nnz_needed.clone() if self._max_needed is None else torch.maximum(self._max_needed, g.nnz_needed)
         return MiniBatch(idx, self.x.index_select(0, idx), g, None if self.y is None else self.y.index_select(0, idx))
 
     def __iter__(self) -> Iterator[MiniBatch]:
         perm = torch.randperm(self.n, device=self.x.device, generator=self.generator)
         for i in range(len(self)):
             yield self.batch(perm[i * self.batch_size:(i + 1) * self.batch_size])
+        self.check()
+
+    def check(self):
+        """Raise if a batch's induced subgraph did not fit `capacity` (its structure was truncated, never overrun).  One device
+        sync: called at the end of every epoch, and by the user after a partial epoch."""
+        if self._max_needed is not None and int(self._max_needed.item()) > self.capacity:
+            raise RuntimeError(f"RandomPartitionSampler: a batch needed {int(self._max_needed.item())} induced edges but capacity is "
+                               f"{self.capacity}; rerun with a larger capacity (or capacity=None for exact sizing)")

@@ -111,6 +111,8 @@ class TransConvLayerBase(_Base):
         if self.use_weight:
             v = Fn.LinearFn.apply(source_input, self.Wv.weight, self.Wv.bias, prec).reshape(-1, self.num_heads, self.out_channels)
         else:
+            if self.num_heads != 1:
+                raise ValueError("use_weight=False requires num_heads == 1 (medium/ours.py:84: V is the single-head layer input)")
             v = source_input.reshape(-1, 1, self.out_channels)
         out = Fn.AttentionFn.apply(q, k, v, prec).mean(dim=1)
         if output_attn:

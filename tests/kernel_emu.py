@@ -10,7 +10,7 @@ from typing import Optional
 
 import torch
 
-EPI_AFFINE, EPI_ATTN_APPLY = 0, 1
+EPI_AFFINE, EPI_ATTN_APPLY, EPI_ATTN_GRAM = 0, 1, 2
 
 
 def _use(t):
@@ -104,7 +104,7 @@ def as_operand(x, planes, memo=False):
 
 def gemm_nt(A, B, pairs, n_out, out, *, epi=EPI_AFFINE, bias=None, aux=None, row_scale=None, alpha=1.0, beta=0.0,
             alpha_dev=None, beta_dev=None, relu=False, accumulate=False, tail=None, nf=0.0, den_out=None, r1_row=None,
-            r1_col=None, col_sum=None, col_sumsq=None):
+            r1_col=None, col_sum=None, col_sumsq=None, nf_dev=None, schedule=None):
     acc = 0
     for (ai, ak, bi, bk, klen) in pairs:
         acc = acc + A[ai].data[:, ak:ak + klen] @ B[bi].data[:, bk:bk + klen].t()
@@ -114,6 +114,11 @@ def gemm_nt(A, B, pairs, n_out, out, *, epi=EPI_AFFINE, bias=None, aux=None, row
         if den_out is not None:
             den_out.copy_(den)
         v = (acc + nf * aux.float()) / den[:, None]
+    elif epi == EPI_ATTN_GRAM:
+        den = (A[0].data @ tail.data.t())[:, 0] + float(nf_dev)
+        if den_out is not None:
+            den_out.copy_(den)
+        v = (acc + bias[:n_out]) / den[:, None]
     else:
         a = alpha * (float(alpha_dev) if alpha_dev is not None else 1.0)
         b = beta * (float(beta_dev) if beta_dev is not None else 1.0)
@@ -154,8 +159,13 @@ def colstats(x, w=None, want_sum=True, want_sumsq=True):
     return s, q
 
 
+def _f(t):
+    """fp32 working precision of the kernels (fp64 inputs stay fp64: the math tests run the same contracts in double)."""
+    return t if t.dtype == torch.float64 else t.float()
+
+
 def _ln_core(x, r, a, b, gamma, beta, use_ln, use_relu):
-    u = a * x.float() + (b * r.float() if r is not None else 0.0)
+    u = a * _f(x) + (b * _f(r) if r is not None else 0.0)
     mean = rstd = None
     xh = u
     if use_ln:
@@ -192,6 +202,28 @@ def ln_bwd(dy, x, r, a, b, gamma, beta, stats, use_ln, use_relu, p, seed, gscale
     dx = _st(new_like(x), a * du)
     dr = _st(new_like(x), b * du) if want_dr else None
     return dx, dr
+
+
+def ln_bwd_attn(dy, o, r, xa, a, b, gamma, beta, stats, use_ln, use_relu, p, seed, gscale, want_dr, dgamma, dbeta, den):
+    """sgf_ln_bwd_attn: LayerNorm backward of u = a*o + b*r fused with the attention-backward row prologue:
+    g = a*du;  gnum' = g/den~;  gden' = -(g.o)/den~;  dr = b*du;  column sums cs = sum gnum', pg = sum xa*gden', sg = sum gden'."""
+    u, xh, t, mean, rstd = _ln_core(o, r, a, b, gamma, beta, use_ln, use_relu)
+    g = gscale * _f(dy)
+    if use_relu:
+        g = g * (t > 0)
+    if use_ln:
+        dgamma += (g * xh).sum(0)
+        dbeta += g.sum(0)
+        gg = g * gamma
+        du = rstd[:, None] * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+    else:
+        du = g
+    ga = a * du
+    gnum_f = ga / den[:, None]
+    gden = -(ga * _f(o)).sum(1) / den
+    gnum = _st(new_like(o), gnum_f)
+    dr = _st(new_like(o), b * du) if want_dr else None
+    return gnum, gden, dr, gnum_f.sum(0), (_f(xa) * gden[:, None]).sum(0), gden.sum().reshape(1)
 
 
 def bn_finalize(sum_, sumsq, rows, h, zbias, running_mean, running_var, device, eps=1e-5, momentum=0.1):
@@ -281,6 +313,64 @@ def axpby(x, y, a, b, out_dtype=None, row_scale=None, out=None):
 
 def head_mean(x, heads, d):
     return _st(alloc_act(x.shape[0], d, x.dtype, x.device), x.float().reshape(x.shape[0], heads, d).mean(1))
+
+
+# ------------------------------------------------------------------------------------------------
+# Gram-form linear attention (sgf_gram, sgf_attn_gram_prepare_fwd/bwd, sgf_ln_bwd_attn): contracts of include/sgformer_b200.h
+# ------------------------------------------------------------------------------------------------
+SC_NQ2, SC_NK2, SC_ALPHA, SC_BETA, SC_DEN, SC_N, SC_IP, SC_C, SC_CQ, SC_CK, SC_SG = 0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12
+
+
+def gram(xop, x):
+    xf = xop.data
+    return xf.t() @ xf, xf.sum(0)
+
+
+class GramState(dict):
+    __getattr__ = dict.__getitem__
+
+
+def attn_gram_prepare_fwd(G, s, wq, bq, wk, bk, wv, bv, n):
+    nf = float(n)
+    kx = wk @ G + torch.outer(bk, s)
+    qx = wq @ G + torch.outer(bq, s)
+    vx = wv @ G + torch.outer(bv, s)
+    z1, q1, v1 = wk @ s + nf * bk, wq @ s + nf * bq, wv @ s + nf * bv
+    S = kx @ wv.t() + torch.outer(z1, bv)
+    nk2 = (kx * wk).sum() + z1 @ bk
+    nq2 = (qx * wq).sum() + q1 @ bq
+    alpha = nq2.rsqrt() * nk2.rsqrt()
+    beta = alpha / nf
+    Bt = beta * (S.t() @ wq) + wv                       # [d, h]: the apply GEMM's B operand (K-major over h)
+    tail = G.new_zeros(16, wq.shape[1])
+    tail[0] = beta * (wq.t() @ z1)
+    bt = beta * (S.t() @ bq) + bv
+    sc = G.new_zeros(16)
+    sc[SC_NQ2], sc[SC_NK2], sc[SC_ALPHA], sc[SC_BETA], sc[SC_DEN], sc[SC_N] = nq2, nk2, alpha, beta, beta * (bq @ z1) + 1.0, nf
+    return GramState(wq=wq, bq=bq, wk=wk, bk=bk, wv=wv, bv=bv, G=G, s=s, kx=kx, qx=qx, vx=vx, z1=z1, q1=q1, v1=v1, S=S, Bt=Bt,
+                     tail=tail, bt=bt, sc=sc, n=n)
+
+
+def attn_gram_prepare_bwd(st, P, pg, cs, sg):
+    """P = x^T gnum' [h,d], pg = x^T gden' [h], cs = colsum(gnum') [d], sg = sum(gden') [1] with gnum' = g/den~, gden' = -(g.o)/den~."""
+    wq, bq, wk, bk, wv, bv = st.wq, st.bq, st.wk, st.bk, st.wv, st.bv
+    S, z1, kx, qx, vx, q1, v1, s = st.S, st.z1, st.kx, st.qx, st.vx, st.q1, st.v1, st.s
+    beta, alpha, nq2, nk2 = st.sc[SC_BETA], st.sc[SC_ALPHA], st.sc[SC_NQ2], st.sc[SC_NK2]
+    dS = wq @ P + torch.outer(bq, cs)
+    dz = wq @ pg + bq * sg
+    c = beta * ((dS * S).sum() + (dz * z1).sum())
+    cq, ck = -c / nq2, -c / nk2
+    dwq = beta * (S @ P.t()) + beta * torch.outer(z1, pg) + cq * qx
+    dbq = beta * (S @ cs + sg * z1) + cq * q1
+    dwk = beta * (dS @ vx) + beta * torch.outer(dz, s) + ck * kx
+    dbk = beta * (dS @ v1) + alpha * dz + ck * z1
+    dwv = beta * (dS.t() @ kx) + P.t()
+    dbv = beta * (dS.t() @ z1) + cs
+    U = dS @ wv
+    A3 = cq * (wq.t() @ wq) + ck * (wk.t() @ wk) + beta * (wk.t() @ U + U.t() @ wk)
+    a4 = cq * (wq.t() @ bq) + ck * (wk.t() @ bk) + beta * (wk.t() @ (dz + dS @ bv) + wv.t() @ (dS.t() @ bk))
+    bcat = torch.cat([st.Bt.t(), A3], 1).contiguous()     # [h, d+h]: B operand of dx = gnum'.Bt + x.A3 (+ gden' (x) tail0 + a4)
+    return dwq, dbq, dwk, dbk, dwv, dbv, bcat, a4
 
 
 def attn_prepare_fwd(s_raw, z_raw, nq2v, nk2v, planes):

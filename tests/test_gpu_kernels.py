@@ -204,6 +204,36 @@ def test_csr_subset_matches_subgraph_then_build(K):
     assert torch.equal(a.data, b_.data)
 
 
+def test_csr_subset_capacity_is_never_overrun(K):
+    """A too-small nnz capacity truncates the batch structure instead of writing past out_col, and is reported."""
+    from sgformer_b200.graph import Graph
+    from sgformer_b200.minibatch import RandomPartitionSampler
+    from sgformer_b200.synth import make_graph
+    n = 6000
+    ei = make_graph(n, 60000, seed=5).to(DEV)
+    full = Graph(ei, n)
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:3000].to(DEV)
+    exact = full.subset(idx)
+    nnz = int(exact.rowptr[-1])
+    assert int(exact.nnz_needed) == nnz
+    cap = nnz // 3
+    node_map = full._node_map
+    rp, cl, dv, needed = K.csr_subset(full.rowptr, full.col, n, idx, node_map, cap + 64)    # buffer has 64 guard entries
+    guard = torch.full((64,), -7, dtype=torch.int32, device=DEV)
+    cl[cap:] = guard
+    rp, cl2, dv, needed = K.csr_subset(full.rowptr, full.col, n, idx, node_map, cap)
+    assert int(needed) == nnz and int(rp[-1]) == cap and int(rp.max()) == cap
+    assert bool((rp[1:] >= rp[:-1]).all())
+    first = int((exact.rowptr <= cap).sum()) - 1             # rows that fit entirely are untouched
+    assert torch.equal(rp[:first + 1], exact.rowptr[:first + 1])
+    assert torch.equal(cl2[:int(rp[first])], exact.col[:int(rp[first])])
+    assert int((node_map != -1).sum()) == 0
+    sampler = RandomPartitionSampler(full, torch.randn(n, 8, device=DEV), None, 3000, capacity=cap)
+    with pytest.raises(RuntimeError, match="capacity"):
+        for _ in sampler:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 # K6/K7: SpMM
 # ------------------------------------------------------------------------------------------------
@@ -565,3 +595,159 @@ def test_attention_partials_vs_fp64(K):
         _close(o.reshape(n, hd, m), ref["out"], 1e-5, 1e-5, "attention out")
         o_b = E.attention_forward(q.to(DEV).bfloat16(), k.to(DEV).bfloat16(), v.to(DEV).bfloat16(), hd, E.BF16, None)
         _close(o_b.float().reshape(n, hd, m), ref["out"], 1e-2, 1e-2, "attention out bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+# Gram-form attention: row prologue, h x h algebra, apply epilogue, and the whole layer against fp64
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,h,n", [(torch.float32, 32, 1000), (torch.bfloat16, 64, 777), (torch.bfloat16, 256, 2500),
+                                       (torch.float32, 256, 300), (torch.bfloat16, 16, 5)])
+def test_ln_bwd_attn(K, dtype, h, n):
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    o, r, dy, xa = _acts(n, h, dtype, 11, 4)
+    g = torch.Generator().manual_seed(3)
+    gamma, beta = 1 + 0.1 * torch.randn(h, generator=g), 0.1 * torch.randn(h, generator=g)
+    den = torch.rand(n, generator=g) + 0.5
+    D = lambda t: None if t is None else t.to(DEV)
+    for use_ln, use_relu, rr, xx in [(True, False, r, r), (True, True, None, xa), (False, True, r, xa), (False, False, r, r)]:
+        _, ste = emu.ln_fwd(o, rr, 0.5, 0.5, gamma, beta, use_ln, use_relu, 0.0, 1)
+        st = D(ste)
+        dg, db = torch.zeros(h, device=DEV), torch.zeros(h, device=DEV)
+        dge, dbe = torch.zeros(h), torch.zeros(h)
+        rd = D(rr)
+        xd = rd if xx is rr else D(xx)          # the residual IS the layer input: same device tensor (aliasing path)
+        gnum, gden, dr, cs, pg, sg = K.ln_bwd_attn(D(dy), D(o), rd, xd, 0.5, 0.5, D(gamma), D(beta), st, use_ln, use_relu, 0.0, 1,
+                                                   0.7, rr is not None, dg, db, D(den))
+        gne, gde, dre, cse, pge, sge = emu.ln_bwd_attn(dy, o, rr, xx, 0.5, 0.5, gamma, beta, ste, use_ln, use_relu, 0.0, 1, 0.7,
+                                                       rr is not None, dge, dbe, den)
+        _close_gated(gnum.float(), gne.float(), tol, tol, f"gnum ln={use_ln}")
+        _close(gden, gde, tol * 4, tol * 4, "gden")
+        if rr is not None:
+            _close_gated(dr.float(), dre.float(), tol, tol, "dr")
+        _close(cs, cse, tol, tol * n ** 0.5, "cs")
+        _close(pg, pge, tol * 4, tol * 4 * n ** 0.5, "pg")
+        _close(sg, sge, tol * 4, tol * 4 * n ** 0.5, "sg")
+        if use_ln:
+            _close(dg, dge, tol, tol * n ** 0.5, "dgamma")
+            _close(db, dbe, tol, tol * n ** 0.5, "dbeta")
+
+
+@pytest.mark.parametrize("h,m,d,n", [(16, 16, 16, 40), (64, 64, 64, 5000), (256, 256, 256, 170000), (100, 100, 100, 900), (8, 8, 8, 3)])
+def test_attn_gram_prepare_vs_fp64(K, h, m, d, n):
+    """sgf_attn_gram_prepare_fwd/_bwd (fp32 SIMT) against the same algebra in fp64 (tests/test_gram_attention_math.py pins it
+    to the reference)."""
+    g = torch.Generator().manual_seed(h + n)
+    x = torch.randn(min(n, 4000), h, generator=g, dtype=torch.float64).clamp_min(-0.5)       # non-zero mean like relu outputs
+    G = (x.t() @ x) * (n / x.shape[0])
+    s = x.sum(0) * (n / x.shape[0])
+    ws = [torch.randn(m, h, generator=g, dtype=torch.float64) / h ** 0.5 for _ in range(2)] + \
+         [torch.randn(d, h, generator=g, dtype=torch.float64) / h ** 0.5]
+    bs = [0.1 * torch.randn(k, generator=g, dtype=torch.float64) for k in (m, m, d)]
+    ref = emu.attn_gram_prepare_fwd(G, s, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2], n)
+    f = lambda t: t.float().to(DEV).contiguous()
+    st = K.attn_gram_prepare_fwd(f(G), f(s), f(ws[0]), f(bs[0]), f(ws[1]), f(bs[1]), f(ws[2]), f(bs[2]), n)
+    for name in ("kx", "qx", "vx", "z1", "q1", "v1", "S", "Bt", "bt"):
+        _close(getattr(st, name), ref[name], 2e-5, 0, name)
+    _close(st.tail[0], ref.tail[0], 5e-5, 0, "ct")
+    assert float(st.tail[1:].abs().max()) == 0.0
+    for slot in (emu.SC_NQ2, emu.SC_NK2, emu.SC_ALPHA, emu.SC_BETA, emu.SC_DEN, emu.SC_N):
+        _close(st.sc[slot], ref.sc[slot], 2e-5, 0, f"sc[{slot}]")
+    # backward with random upstream contractions of the right magnitude
+    P = torch.randn(h, d, generator=g, dtype=torch.float64) * n ** 0.5
+    pg, cs = torch.randn(h, generator=g, dtype=torch.float64) * n ** 0.5, torch.randn(d, generator=g, dtype=torch.float64) * n ** 0.5
+    sg = torch.randn(1, generator=g, dtype=torch.float64) * n ** 0.5
+    refb = emu.attn_gram_prepare_bwd(ref, P, pg, cs, sg)
+    got = K.attn_gram_prepare_bwd(st, f(P), f(pg), f(cs), f(sg))
+    for name, a, b in zip(("dWq", "dbq", "dWk", "dbk", "dWv", "dbv", "bcat", "a4"), got, refb):
+        # relative to the largest entry: the q/k gradients are differences of O(1/N) terms
+        _close(a, b, 2e-4, 0, name)
+
+
+@pytest.mark.parametrize("rows,h,d", [(64, 16, 16), (1000, 64, 64), (3000, 256, 256), (130, 32, 32), (5000, 100, 100)])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_gemm_nt_attention_gram_epilogue(K, rows, h, d, planes):
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(rows, h, generator=g)
+    bt_m, tail = torch.randn(d, h, generator=g) / h ** 0.5, torch.zeros(16, h)
+    tail[0] = 0.01 * torch.randn(h, generator=g)
+    bias, dconst = torch.randn(d, generator=g), torch.tensor([1.25])
+    X, Xe = K.pack_operand(x.to(DEV), False, planes), emu.pack_operand(x, False, planes)
+    B, T = K.pack_operand(bt_m.to(DEV), False, planes), K.pack_operand(tail.to(DEV), False, planes)
+    Be, Te = emu.pack_operand(bt_m, False, planes), emu.pack_operand(tail, False, planes)
+    for dt in ([torch.float32, torch.bfloat16] if planes == 1 else [torch.float32]):
+        out = K.alloc_act(rows, d, dt, DEV)
+        den = torch.empty(rows, device=DEV)
+        K.gemm_nt([X], [B], [(0, 0, 0, 0, h)], d, out, epi=2, bias=bias.to(DEV), tail=T, nf_dev=dconst.to(DEV), den_out=den)
+        oe, de = torch.zeros(rows, d), torch.zeros(rows)
+        emu.gemm_nt([Xe], [Be], [(0, 0, 0, 0, h)], d, oe, epi=2, bias=bias, tail=Te, nf_dev=dconst, den_out=de)
+        tol = 2e-5 if planes == 3 else (2e-3 if dt == torch.float32 else 1e-2)
+        _close(den, de, tol, tol, "den")
+        _close(out.float(), oe, tol, tol, f"gram apply {dt}")
+
+
+@pytest.mark.parametrize("n,h,use_weight,residual", [(16, 8, True, True), (257, 32, True, False), (4000, 256, True, True),
+                                                      (1500, 64, False, True), (30000, 128, True, True)])
+def test_gram_attention_layer_vs_fp64(K, n, h, use_weight, residual):
+    """Whole single-head TransConv layer (projections + full_attention_conv + residual + LayerNorm) forward and backward
+    on the device against fp64 autograd of the reference formula; attention term checked with RELATIVE tolerances at small N."""
+    from sgformer_b200 import engine as E
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, h, generator=g).clamp_min(-0.3)
+    P64, P = {}, {}
+    lp = "convs.0."
+    for nm in ("Wq", "Wk") + (("Wv",) if use_weight else ()):
+        P64[lp + nm + ".weight"] = (torch.randn(h, h, generator=g, dtype=torch.float64) / h ** 0.5).requires_grad_(True)
+        P64[lp + nm + ".bias"] = (0.1 * torch.randn(h, generator=g, dtype=torch.float64)).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(h, generator=g, dtype=torch.float64)).requires_grad_(True)
+    beta = (0.1 * torch.randn(h, generator=g, dtype=torch.float64)).requires_grad_(True)
+    for k_, v in P64.items():
+        P[k_] = v.detach().float().to(DEV)
+    x64 = x.double().requires_grad_(True)
+    q = x64 @ P64[lp + "Wq.weight"].t() + P64[lp + "Wq.bias"]
+    k = x64 @ P64[lp + "Wk.weight"].t() + P64[lp + "Wk.bias"]
+    v = x64 @ P64[lp + "Wv.weight"].t() + P64[lp + "Wv.bias"] if use_weight else x64
+    qs, ks = q / torch.norm(q), k / torch.norm(k)
+    o64 = (qs @ (ks.t() @ v) + n * v) / (qs @ ks.sum(0) + n)[:, None]
+    ca, cb = (0.5, 0.5) if residual else (1.0, 0.0)
+    u = ca * o64 + (cb * x64 if residual else 0.0)
+    y64 = torch.nn.functional.layer_norm(u, (h,), gamma, beta, 1e-5)
+    w = torch.randn(n, h, generator=g, dtype=torch.float64)
+    (y64 * w).sum().backward()
+
+    for prec, tol_o, tol_g in ((E.FP32, 1e-4, 3e-3), (E.BF16, 1e-2, 6e-2)):
+        xa = x.to(DEV).to(prec.act_dtype)
+        K.operand_memo_begin()
+        tape = E.Tape()
+        o = E.attention_gram_forward(P, lp, xa, use_weight, prec, tape)
+        _close(o.float(), o64.detach(), tol_o, tol_o, f"{prec.name} attention output")
+        if prec is E.FP32:
+            # attention term alone (out - v), relative: invisible behind N*v at the output (SURVEY.md §7 hard part 1)
+            att = o.double().cpu() - v.detach()
+            att64 = (o64 - v).detach()
+            if n <= 300:
+                _close(att, att64, 2e-3, 0, "attention term (relative)")
+            _close(tape["st"].S, (k.t() @ v).detach(), 5e-5, 0, "S' = k^T v")
+            _close(tape["st"].z1, k.sum(0).detach(), 5e-5, 0, "z' = k^T 1")
+            _close(tape["st"].sc[K.SC_NQ2], (q * q).sum().detach(), 5e-5, 0, "||q||^2")
+            _close(tape["st"].sc[K.SC_NK2], (k * k).sum().detach(), 5e-5, 0, "||k||^2")
+        y, stt = K.ln_fwd(o, xa if residual else None, ca, cb, gamma.detach().float().to(DEV), beta.detach().float().to(DEV), True,
+                          False, 0.0, 1)
+        _close(y.float(), y64.detach(), tol_o * 3, tol_o * 3, f"{prec.name} layer output")
+        dg, db = torch.zeros(h, device=DEV), torch.zeros(h, device=DEV)
+        dy = w.float().to(DEV).to(prec.act_dtype)
+        gnum, gden, dr, cs, pg, sg = K.ln_bwd_attn(dy, o, xa if residual else None, xa, ca, cb, gamma.detach().float().to(DEV),
+                                                   beta.detach().float().to(DEV), stt, True, False, 0.0, 1, 1.0, residual, dg, db,
+                                                   tape["den"])
+        grads = {}
+        dprev = dr if dr is not None else K.new_like(xa)
+        E.attention_gram_backward(P, lp, tape, xa, gnum, gden, cs, pg, sg, use_weight, prec, dprev, dr is not None, grads)
+        K.operand_memo_clear()
+        _close(dprev.float(), x64.grad, tol_g, tol_g * 0.1, f"{prec.name} dx")
+        _close(dg, gamma.grad, tol_g, tol_g, "dgamma")
+        _close(db, beta.grad, tol_g, tol_g, "dbeta")
+        if use_weight:
+            _close(grads[lp + "Wv.weight"], P64[lp + "Wv.weight"].grad, tol_g, 0, f"{prec.name} dWv")
+            _close(grads[lp + "Wv.bias"], P64[lp + "Wv.bias"].grad, tol_g, 0, f"{prec.name} dbv")
+        if prec is E.FP32 and n <= 300:      # q/k gradients are O(1/N) relative: only pinned where the attention term is visible
+            for nm in ("Wq.weight", "Wq.bias", "Wk.weight", "Wk.bias"):
+                _close(grads[lp + nm], P64[lp + nm].grad, 2e-2, 0, f"fp32 d{nm}")
