@@ -319,6 +319,13 @@ int sgf_attn_prepare_bwd(const float* s_raw, const float* z_raw, const float* ds
  * All pointers are DEVICE fp32, row-major and dense unless a pitch is given.  use_weight=False (V = x, medium/ours.py:84) is
  * expressed by passing the identity as wv and zeros as bv.
  * ------------------------------------------------------------------------------------------------ */
+/* Pass 1: G[h,h] = X^T X (fp32, both triangles, pitch ldg) and s[h] = X^T 1 of a bf16 tensor-core operand X [rows, h <= 256]
+ * (planes = 1: one bf16 plane; planes = 3: bf16x3 planes side by side, plane_ld elements apart, the six partial products are
+ * accumulated).  tcgen05 kernel that loads every tile once for both MMA operands and accumulates only the upper block
+ * triangle; deterministic two-stage reduction through ws (sgf_gram_ws_bytes). */
+int sgf_gram_ws_bytes(int32_t h, int32_t planes, int64_t rows, size_t* bytes);
+int sgf_gram(const void* x, int64_t ldx, int64_t rows, int32_t h, int32_t planes, int64_t plane_ld, float* G, int64_t ldg,
+             float* s, void* ws, size_t ws_bytes, void* stream);
 typedef struct {
     int32_t h, m, d;            /* input width, q/k width (Wq, Wk: [m,h]), v width (Wv: [d,h]) */
     int64_t n_nodes;            /* N of `N*vs` / `+N` (medium/ours.py:25,31): the GLOBAL node count when row-sharded */
@@ -357,6 +364,27 @@ int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, const void* xa
                     float a, float b, const float* gamma, const float* beta, const float* stats, int use_ln, int use_relu,
                     float p, uint64_t seed, float gscale, const float* den, void* gnum, float* gden, void* dr, float* dgamma,
                     float* dbeta, float* cs, float* pg, float* sg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused two-group Adam (replaces torch.optim.Adam([{params1, trans_weight_decay}, {params2,
+ * gnn_weight_decay}], lr) of large/main.py:115-119 and its optimizer.step() at :142): all tensors of a step in one launch per
+ * SGF_ADAM_MAX_TENSORS, fp32 parameters / gradients / moments, hyper-parameters per tensor (its group's), the step count t
+ * on the device (fp32 scalar advanced by sgf_adam_tick, so CUDA-graph replays keep counting).
+ *   g += wd*p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * ------------------------------------------------------------------------------------------------ */
+#define SGF_ADAM_MAX_TENSORS 32
+typedef struct {
+    int32_t n_tensors;
+    float* param[SGF_ADAM_MAX_TENSORS]; const float* grad[SGF_ADAM_MAX_TENSORS];
+    float* exp_avg[SGF_ADAM_MAX_TENSORS]; float* exp_avg_sq[SGF_ADAM_MAX_TENSORS];
+    int64_t numel[SGF_ADAM_MAX_TENSORS];
+    float lr[SGF_ADAM_MAX_TENSORS], beta1[SGF_ADAM_MAX_TENSORS], beta2[SGF_ADAM_MAX_TENSORS], eps[SGF_ADAM_MAX_TENSORS],
+          weight_decay[SGF_ADAM_MAX_TENSORS];
+    const float* step;                          /* device fp32 scalar: t of THIS update (>= 1) */
+    int32_t chunk0[SGF_ADAM_MAX_TENSORS + 1];   /* filled by sgf_adam_step */
+} sgf_adam_args;
+int sgf_adam_tick(float* step /* device */, void* stream);      /* *step += 1 */
+int sgf_adam_step(sgf_adam_args* args /* host, chunk0 is written */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,22 @@ class AttnGramArgs(C.Structure):
     ]
 
 
+SGF_ADAM_MAX_TENSORS = 32
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [
+        ("n_tensors", _i32),
+        ("param", _vp * SGF_ADAM_MAX_TENSORS), ("grad", _vp * SGF_ADAM_MAX_TENSORS),
+        ("exp_avg", _vp * SGF_ADAM_MAX_TENSORS), ("exp_avg_sq", _vp * SGF_ADAM_MAX_TENSORS),
+        ("numel", _i64 * SGF_ADAM_MAX_TENSORS),
+        ("lr", _f32 * SGF_ADAM_MAX_TENSORS), ("beta1", _f32 * SGF_ADAM_MAX_TENSORS), ("beta2", _f32 * SGF_ADAM_MAX_TENSORS),
+        ("eps", _f32 * SGF_ADAM_MAX_TENSORS), ("weight_decay", _f32 * SGF_ADAM_MAX_TENSORS),
+        ("step", _vp),
+        ("chunk0", _i32 * (SGF_ADAM_MAX_TENSORS + 1)),
+    ]
+
+
 class GemmTnArgs(C.Structure):
     _fields_ = [
         ("a", _vp), ("lda", _i64), ("m", _i32),
@@ -93,9 +109,13 @@ _SIGS = {
                              _f32, _u64, _f32, _vp, _vp, _vp, _vp, _vp]),
     "sgf_ln_bwd_attn": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, C.c_int, C.c_int,
                                   _f32, _u64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sgf_gram_ws_bytes": (C.c_int, [_i32, _i32, _i64, C.POINTER(_sz)]),
+    "sgf_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "sgf_attn_gram_ws_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_i64)]),
     "sgf_attn_gram_prepare_fwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
     "sgf_attn_gram_prepare_bwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
+    "sgf_adam_tick": (C.c_int, [_vp, _vp]),
+    "sgf_adam_step": (C.c_int, [C.POINTER(AdamArgs), _vp]),
     "sgf_bn_finalize": (C.c_int, [_vp, _vp, _i64, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgf_bn_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                              _f32, _u64, _f32, _vp, _vp, _vp, _vp]),

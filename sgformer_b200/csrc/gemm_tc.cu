@@ -778,6 +778,202 @@ __global__ void tn_reduce_kernel(const float* __restrict__ ws, int nparts, int m
     }
 }
 }  // namespace tn
+// ================================================================================================
+// gram : G[h,h] = X^T X and s[h] = X^T 1 of one bf16 operand X [rows, h <= 256] — pass 1 of the Gram-form attention
+// ================================================================================================
+// The node-contracting product of gemm_tn specialised for A == B (reference contractions it replaces: k^T v, k^T 1, ||q||^2,
+// ||k||^2 of medium/ours.py:16-31 — all functions of X^T X, see csrc/attn_gram.cu):
+//  * every [64 feat x 64 node] box is loaded ONCE and feeds both operands of the MMA (A and B descriptors point at the same
+//    shared-memory tile), so the kernel moves rows*h*2 bytes for 2*rows*h^2 flops (AI = h flop/B: 256 at h = 256, at the
+//    bf16 ridge) instead of twice that;
+//  * G is symmetric: only the blocks (0,0), (0,1) and (1,1) of the 2 x 2 block matrix are accumulated
+//    (M=128 x N=256 + M=128 x N=128 per k-step: 3/4 of the flops, 384 TMEM columns), the reduction kernel mirrors (0,1);
+//  * X^T 1 rides along as an N = 16 MMA against a constant all-ones tile (16 more TMEM columns per row block);
+//  * bf16x3 operands (fp32 mode): the six plane pairs of kernels._PAIRS3 accumulate into the same TMEM tiles.
+// The node range is split across the CTAs; per-CTA partials -> workspace -> fixed-order reduction (deterministic).
+namespace gramk {
+constexpr int BKN = 64, THREADS = 192;
+constexpr int CHUNK_BYTES = 64 * BKN * 2;        // one [64 feat x 64 node] box = 8 KB
+constexpr int ONES_BYTES = CHUNK_BYTES;          // constant tile of bf16 1.0
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;          // stages * planes * chunks * 8 KB
+constexpr int MAX_STAGES = 8;
+
+struct Params {
+    int64_t rows, kb_total;
+    int h, chunks, m_blocks, un, n_planes, stages;
+    int plane_off[3];                             // column offset (elements) of each plane
+    int n_pairs, pa[6], pb[6];
+    int ncols;                                    // fp32 columns per CTA partial: un + (un - 128 if m_blocks == 2) + m_blocks
+    float* ws;                                    // [grid][ncols][128]
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gram_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int plane_bytes = p.chunks * CHUNK_BYTES;
+    const int stage_bytes = p.n_planes * plane_bytes;
+    uint8_t* ones = smem + p.stages * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tmem_full = empty + MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    static_assert((2 * MAX_STAGES + 1) * 8 + 4 <= BAR_BYTES, "barrier area");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t per = p.kb_total / gridDim.x, rem = p.kb_total % gridDim.x;
+    const int64_t kb0 = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
+    const int64_t kb1 = kb0 + per + (blockIdx.x < rem ? 1 : 0);
+
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;   // bf16 1.0 x2
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();        // the generic-proxy writes of the ones tile must be visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: [0, un) block row 0 | [256, 256 + un - 128) block (1,1) | 384 + 16*mb: X^T 1
+    constexpr uint32_t COL_D1 = 256, COL_S = 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * stage_bytes;
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                for (int pl = 0; pl < p.n_planes; ++pl)
+                    for (int c = 0; c < p.chunks; ++c)
+                        tma_load_2d(sa + pl * plane_bytes + c * CHUNK_BYTES, &tm, &full[stage], p.plane_off[pl] + c * 64, (int32_t)(kb * BKN));
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc0 = make_idesc_bf16(128, p.un, 1, 1);                                   // both operands MN-major
+            const uint32_t idesc1 = make_idesc_bf16(128, p.m_blocks == 2 ? p.un - 128 : 16, 1, 1);
+            const uint32_t idescs = make_idesc_bf16(128, 16, 1, 1);
+            const uint32_t s_ones = smem_u32(ones);
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                for (int pr = 0; pr < p.n_pairs; ++pr) {
+                    const uint32_t a0 = sa + p.pa[pr] * plane_bytes, b0 = sa + p.pb[pr] * plane_bytes;
+#pragma unroll
+                    for (int k = 0; k < BKN / 16; ++k) {
+                        // MN-major SW128: LBO = stride between 64-element feature chunks, SBO = stride between 8-row node groups
+                        const uint32_t accum = (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t da0 = make_smem_desc_sw128(a0 + k * 2048, CHUNK_BYTES, 1024);
+                        const uint64_t db0 = make_smem_desc_sw128(b0 + k * 2048, CHUNK_BYTES, 1024);
+                        umma_bf16(tmem_base, da0, db0, idesc0, accum);
+                        if (p.m_blocks == 2) {
+                            const uint64_t da1 = make_smem_desc_sw128(a0 + 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
+                            const uint64_t db1 = make_smem_desc_sw128(b0 + 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
+                            umma_bf16(tmem_base + COL_D1, da1, db1, idesc1, accum);
+                        }
+                    }
+                }
+                for (int pl = 0; pl < p.n_planes; ++pl) {
+                    const uint32_t a0 = sa + pl * plane_bytes;
+#pragma unroll
+                    for (int k = 0; k < BKN / 16; ++k) {
+                        const uint32_t accum = (kb > kb0 || pl > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t dones = make_smem_desc_sw128(s_ones + k * 2048, CHUNK_BYTES, 1024);
+                        for (int mb = 0; mb < p.m_blocks; ++mb) {
+                            const uint64_t da = make_smem_desc_sw128(a0 + mb * 2 * CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024);
+                            umma_bf16(tmem_base + COL_S + 16 * mb, da, dones, idescs, accum);
+                        }
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (kb == kb1 - 1) umma_commit(tmem_full);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int l = q * 32 + lane;
+        float* ws = p.ws + (int64_t)blockIdx.x * p.ncols * 128;
+        const bool any = kb1 > kb0;
+        if (any) {
+            mbar_wait(tmem_full, 0);
+            tcgen05_fence_after();
+        }
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        auto dump = [&](uint32_t tcol, int ncol16, int ws_col0) {
+            for (int c = 0; c < ncol16; ++c) {
+                float v[16];
+                if (any) {
+                    __syncwarp();
+                    tmem_ld16(tlane + tcol + c * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ws[(int64_t)(ws_col0 + c * 16 + j) * 128 + l] = v[j];
+            }
+        };
+        dump(0, p.un / 16, 0);
+        int col = p.un;
+        if (p.m_blocks == 2) { dump(COL_D1, (p.un - 128) / 16, col); col += p.un - 128; }
+        for (int mb = 0; mb < p.m_blocks; ++mb) {
+            float v[16];
+            if (any) {
+                __syncwarp();
+                tmem_ld16(tlane + COL_S + 16 * mb, v);
+                tmem_ld_wait();
+            } else {
+                v[0] = 0.f;
+            }
+            ws[(int64_t)(col + mb) * 128 + l] = v[0];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// G (both triangles) and s from the per-CTA partials, summed in CTA order (deterministic)
+__global__ void gram_reduce_kernel(const float* __restrict__ ws, int nparts, int ncols, int un, int m_blocks, int h, float* __restrict__ G,
+                                   int64_t ldg, float* __restrict__ s) {
+    const int total = ncols * 128;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c = t / 128, l = t % 128;
+        float acc = 0.f;
+        for (int part = 0; part < nparts; ++part) acc += ws[((int64_t)part * ncols + c) * 128 + l];
+        if (c < un) {                                       // block row 0: G[l][c], mirrored into block (1,0)
+            if (l < h && c < h) {
+                G[(int64_t)l * ldg + c] = acc;
+                if (m_blocks == 2 && c >= 128) G[(int64_t)c * ldg + l] = acc;
+            }
+        } else if (m_blocks == 2 && c < un + (un - 128)) {   // block (1,1)
+            const int i = 128 + l, j = 128 + (c - un);
+            if (i < h && j < h) G[(int64_t)i * ldg + j] = acc;
+        } else {                                            // X^T 1
+            const int mb = c - (ncols - m_blocks);
+            const int i = mb * 128 + l;
+            if (i < h) s[i] = acc;
+        }
+    }
+}
+}  // namespace gramk
 }  // namespace sgf
 
 using namespace sgf;
@@ -985,6 +1181,73 @@ extern "C" int sgf_gemm_tn(const sgf_gemm_tn_args* a, void* stream) {
     int rgrid = (int)((total + 255) / 256);
     tn::tn_reduce_kernel<<<rgrid, 256, 0, st>>>(p.ws, grid, mp, p.un, a->m, a->n, a->alpha, a->alpha_dev, a->beta, a->out, a->ldo,
                                                 a->transpose_out);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+
+static int gram_geometry(int h, int planes, int64_t rows, gramk::Params& p) {
+    if (h <= 0 || h > 256 || (planes != 1 && planes != 3) || rows < 0) return SGF_ERR_ARG;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows; p.h = h;
+    p.chunks = (h + 63) / 64;
+    p.m_blocks = h > 128 ? 2 : 1;
+    p.un = (h + 15) / 16 * 16;
+    p.n_planes = planes;
+    p.kb_total = (rows + gramk::BKN - 1) / gramk::BKN;
+    p.stages = gramk::SMEM_BUDGET / (planes * p.chunks * gramk::CHUNK_BYTES);
+    if (p.stages > gramk::MAX_STAGES) p.stages = gramk::MAX_STAGES;
+    if (p.stages < 2) return SGF_ERR_UNSUPPORTED;
+    p.ncols = p.un + (p.m_blocks == 2 ? p.un - 128 : 0) + p.m_blocks;
+    return SGF_OK;
+}
+static inline int gram_grid(int64_t kb_total) { return (int)(kb_total < num_sms() ? (kb_total < 1 ? 1 : kb_total) : num_sms()); }
+
+extern "C" int sgf_gram_ws_bytes(int32_t h, int32_t planes, int64_t rows, size_t* bytes) {
+    gramk::Params p;
+    int rc = gram_geometry(h, planes, rows, p);
+    if (rc || !bytes) return rc ? rc : SGF_ERR_ARG;
+    *bytes = (size_t)gram_grid(p.kb_total) * p.ncols * 128 * sizeof(float);
+    return SGF_OK;
+}
+
+extern "C" int sgf_gram(const void* x, int64_t ldx, int64_t rows, int32_t h, int32_t planes, int64_t plane_ld, float* G, int64_t ldg,
+                        float* s, void* ws, size_t ws_bytes, void* stream) {
+    gramk::Params p;
+    int rc = gram_geometry(h, planes, rows, p);
+    if (rc) return rc;
+    if (!x || !G || !s || !ws || ldg < h || (planes == 3 && (plane_ld < h || plane_ld % 64 != 0))) return SGF_ERR_ARG;
+    size_t need = 0;
+    sgf_gram_ws_bytes(h, planes, rows, &need);
+    if (ws_bytes < need) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.ws = (float*)ws;
+    for (int i = 0; i < planes; ++i) p.plane_off[i] = (int)(i * plane_ld);
+    if (planes == 1) {
+        p.n_pairs = 1;
+    } else {      // bf16x3: the six partial products, smallest terms first (kernels._PAIRS3)
+        static const int PA[6] = {0, 2, 1, 0, 1, 0}, PB[6] = {2, 0, 1, 1, 0, 0};
+        p.n_pairs = 6;
+        for (int i = 0; i < 6; ++i) { p.pa[i] = PA[i]; p.pb[i] = PB[i]; }
+    }
+    const int grid = gram_grid(p.kb_total);
+    if (rows > 0) {
+        CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        const int64_t span = planes == 1 ? h : 2 * plane_ld + h;
+        if ((rc = make_tmap_bf16(&tm, x, rows, span, ldx, gramk::BKN))) return rc;
+        const int smem_bytes = p.stages * planes * p.chunks * gramk::CHUNK_BYTES + gramk::ONES_BYTES + gramk::BAR_BYTES + 1024;
+        static int attr_set = 0;
+        if (attr_set < smem_bytes) {
+            SGF_CUDA_TRY(cudaFuncSetAttribute(gramk::gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = 227 * 1024;
+        }
+        gramk::gram_kernel<<<grid, gramk::THREADS, smem_bytes, st>>>(tm, p);
+        SGF_LAUNCH_CHECK(); count_launch();
+    } else {
+        SGF_CUDA_TRY(cudaMemsetAsync(ws, 0, need, st));
+    }
+    gramk::gram_reduce_kernel<<<(p.ncols * 128 + 255) / 256, 256, 0, st>>>(p.ws, grid, p.ncols, p.un, p.m_blocks, h, G, ldg, s);
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

@@ -693,10 +693,26 @@ def attn_combine_scal(scal_bwd_all: Tensor, heads: int, scal_fwd: Tensor):
 SC_NQ2, SC_NK2, SC_ALPHA, SC_BETA, SC_DEN, SC_N, SC_IP, SC_C, SC_CQ, SC_CK, SC_SG = 0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12
 
 
+GRAM_KERNEL = os.environ.get("SGF_GRAM_KERNEL", "1") == "1"
+
+
 def gram(xop: Operand, x: Tensor):
-    """Pass 1 of the Gram-form attention: G = x^T x (fp32 [h,h]) and s = x^T 1 (fp32 [h]) of the layer input."""
+    """Pass 1 of the Gram-form attention: G = x^T x (fp32 [h,h]) and s = x^T 1 (fp32 [h]) of the layer input.
+    h <= 256: sgf_gram (one load per tile, upper block triangle, X^T 1 as an extra MMA column); wider layers: the generic
+    node-contracting GEMM + a column-sum pass."""
     h = xop.k
-    G = torch.empty((h, h), dtype=torch.float32, device=x.device)
+    dev = x.device
+    if h <= 256 and GRAM_KERNEL:
+        _use(xop.data)
+        G = torch.empty((h, h), dtype=torch.float32, device=dev)
+        s = torch.empty(h, dtype=torch.float32, device=dev)
+        nbytes = C.c_size_t(0)
+        check(lib().sgf_gram_ws_bytes(h, xop.planes, xop.rows, C.byref(nbytes)), "sgf_gram_ws_bytes")
+        ws = torch.empty(max(nbytes.value, 4), dtype=torch.uint8, device=dev)
+        check(lib().sgf_gram(_p(xop.data), xop.ld, xop.rows, h, xop.planes, xop.kp if xop.planes == 3 else 0, _p(G), h, _p(s), _p(ws),
+                             nbytes.value, _stream()), "sgf_gram")
+        return G, s
+    G = torch.empty((h, h), dtype=torch.float32, device=dev)
     gemm_tn(xop, xop, G)
     s, _ = colstats(x, want_sumsq=False)
     return G, s

@@ -1,5 +1,9 @@
 """torchrun script (not a pytest file): row-sharded execution on N GPUs over NCCL must reproduce the single-GPU result.
-Run by scripts/gpu_multi_bench.sh:  torchrun --nproc-per-node N tests/multi_gpu_check.py"""
+Run by tests/test_gpu_multi.py (pytest -m gpu on a box with >= 2 GPUs) and scripts/gpu_multi_*.sh:
+    torchrun --nproc-per-node N tests/multi_gpu_check.py
+Logits 2e-4 (fp32) / 2e-2 (bf16) of the largest logit; EVERY parameter gradient (weights and biases) within 1e-3 (fp32) /
+5e-2 (bf16) of max(its own scale, 1e-3 of the model's largest gradient entry) - biases in front of a BatchNorm have an
+analytically zero gradient, so their scale is pure rounding noise."""
 import os
 import sys
 
@@ -42,14 +46,17 @@ def main():
         out = shard(x[r0:r1].contiguous(), ei)
         (torch.nn.functional.nll_loss(torch.log_softmax(out, 1), y[r0:r1], reduction="sum") / n).backward()
         err = (out - out_ref[r0:r1]).abs().max().item() / out_ref.abs().max().item()
-        gerr = 0.0
+        gabs = max(q.grad.abs().max().item() for q in ref.parameters())
+        gerr, worst = 0.0, ""
         for (k, p), (_, q) in zip(shard.named_parameters(), ref.named_parameters()):
-            scale = max(q.grad.abs().max().item(), 1e-6)
-            gerr = max(gerr, (p.grad - q.grad).abs().max().item() / scale) if "bias" not in k else gerr
-        good = err <= tol and gerr <= (2e-2 if prec == "fp32" else 0.3)
+            scale = max(q.grad.abs().max().item(), 1e-3 * gabs)
+            e = (p.grad - q.grad).abs().max().item() / scale
+            if e > gerr:
+                gerr, worst = e, k
+        good = err <= tol and gerr <= (1e-3 if prec == "fp32" else 5e-2)
         ok = ok and good
         if rank == 0:
-            print(f"[{prec}] world={world}: logits rel err {err:.3e}, worst weight-grad rel err {gerr:.3e} -> {'OK' if good else 'FAIL'}")
+            print(f"[{prec}] world={world}: logits rel err {err:.3e}, worst parameter-grad rel err {gerr:.3e} ({worst}) -> {'OK' if good else 'FAIL'}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -751,3 +751,27 @@ def test_gram_attention_layer_vs_fp64(K, n, h, use_weight, residual):
         if prec is E.FP32 and n <= 300:      # q/k gradients are O(1/N) relative: only pinned where the attention term is visible
             for nm in ("Wq.weight", "Wq.bias", "Wk.weight", "Wk.bias"):
                 _close(grads[lp + nm], P64[lp + nm].grad, 2e-2, 0, f"fp32 d{nm}")
+
+
+@pytest.mark.parametrize("rows,h", [(1, 16), (63, 64), (64, 64), (1000, 128), (20000, 256), (5000, 100), (4097, 200), (300000, 256),
+                                    (777, 8)])
+@pytest.mark.parametrize("planes", [1, 3])
+def test_gram_kernel(K, monkeypatch, rows, h, planes):
+    """sgf_gram (X^T X with one operand load, upper block triangle mirrored, X^T 1 as an MMA column) against fp64, and against
+    the generic node-contracting GEMM path; deterministic."""
+    g = torch.Generator().manual_seed(rows + h)
+    x = (torch.randn(rows, h, generator=g) + 0.3)
+    xd = x.to(DEV)
+    X = K.pack_operand(xd, False, planes)
+    xe = emu.pack_operand(x, False, planes).data.double()
+    G, s = K.gram(X, xd)
+    tol = 2e-5 if planes == 3 else 1e-2
+    _close(G, xe.t() @ xe, tol, tol * rows ** 0.5, "G = X^T X")
+    _close(s, xe.sum(0), tol, tol * rows ** 0.5, "s = X^T 1")
+    _close(G, G.t(), 1e-6, 0, "G symmetric")
+    G2, s2 = K.gram(X, xd)
+    assert torch.equal(G, G2) and torch.equal(s, s2), "sgf_gram must be run-to-run deterministic"
+    monkeypatch.setattr(K, "GRAM_KERNEL", False)
+    Gl, sl = K.gram(X, xd if planes == 3 else xd.bfloat16())
+    _close(G, Gl, tol, tol * rows ** 0.5, "dedicated kernel vs gemm_tn path")
+    _close(s, sl, tol, tol * rows ** 0.5, "s vs colstats path")
