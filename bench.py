@@ -348,7 +348,7 @@ def run_full_batch(ctx, wname, w, parallel, steps, warmup, want_e2e=False, want_
             print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
             torch.cuda.synchronize()
             run_step = lambda: step(x, ei, y)  # noqa: E731
-    graph = get_graph(ei, n, 0, rows=comm.rows) if rows_mode else get_graph(ei, n, 0)
+    graph = get_graph(ei, n, 0, rows=comm.rows, col_rot=comm.col_rot) if rows_mode else get_graph(ei, n, 0)
     nnz = graph.nnz
     sampler = ClockSampler(ctx.local) if (rank == 0 and sample_clocks) else None
     if sampler:

@@ -64,6 +64,14 @@ int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_t row_begin
                        int by_source, int self_loop_mode, int64_t* rowptr, int32_t* col, float* dinv, void* ws,
                        size_t ws_bytes, void* stream);
 
+/* As sgf_csr_build_rect with ROTATED column ids col' = (col - col_rot) mod col_mod (col_mod >= n_cols; col_mod = 0: no rotation),
+ * rows sorted by col'.  A row shard built with col_rot = row_begin, col_mod = world * ceil(n/world) has its own row block first in
+ * every row, then the blocks of rank+1, rank+2, ...: the order in which sgf_spmm_flagged consumes the operand blocks that the
+ * peers push over NVLink (slot s of the gathered buffer = block of rank (rank + s) mod world). */
+int sgf_csr_build_rot(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols, int by_source,
+                      int self_loop_mode, int64_t col_rot, int64_t col_mod, int64_t* rowptr, int32_t* col, float* dinv, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* K9 — induced subgraph with relabelling (replaces PyG subgraph(idx, edge_index, num_nodes=n,
  * relabel_nodes=True) at large/main-batch.py:139 / large/eval.py:89): keeps edges whose endpoints are
  * both in `subset` and maps node ids to positions in `subset`.  Output order = input edge order
@@ -118,6 +126,20 @@ int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, 
 int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y, int64_t ldy, int h,
                    int dtype, const int64_t* seg_start, const int32_t* seg_len, int64_t n_seg, float* partial,
                    const int64_t* heavy_rows, const int64_t* heavy_seg_ptr, int64_t n_heavy, void* stream);
+
+/* Row-sharded SpMM fused with the halo exchange: as sgf_spmm, but x is the gathered operand
+ * [n_slots*slot_rows, h] of which only slot 0 (this rank's own rows) is present at launch; slot s > 0 (the rows of rank
+ * (rank + s) mod world) is being written by that rank over NVLink (copy-engine peer copy into this buffer) and is complete once
+ * flags[s] != 0 (the sender's sgf_signal after its copy).  col holds ROTATED ids (sgf_csr_build_rot), so every row meets its
+ * neighbours in slot order and a warp only waits the first time it touches a slot that has not landed: the gather of the local and
+ * the already-arrived blocks overlaps the transfer of the rest.  One wave of resident CTAs; flags[0] is ignored. */
+int sgf_spmm_flagged(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y,
+                     int64_t ldy, int64_t n_rows, int h, int dtype, int64_t max_row_len, const uint32_t* flags, int64_t slot_rows,
+                     int n_slots, void* stream);
+/* *flag = value with release semantics at system scope (flag may live in a peer GPU's memory): "my block has landed". */
+int sgf_signal(uint32_t* flag, uint32_t value, void* stream);
+/* returns (on the stream) once flags[0..n) are all non-zero */
+int sgf_wait_flags(const uint32_t* flags, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 tensor cores (bf16 operands staged by TMA, fp32 accumulation in TMEM).
@@ -368,8 +390,9 @@ int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, const void* xa
 /* ------------------------------------------------------------------------------------------------
  * Fused two-group Adam (replaces torch.optim.Adam([{params1, trans_weight_decay}, {params2,
  * gnn_weight_decay}], lr) of large/main.py:115-119 and its optimizer.step() at :142): all tensors of a step in one launch per
- * SGF_ADAM_MAX_TENSORS, fp32 parameters / gradients / moments, hyper-parameters per tensor (its group's), the step count t
- * on the device (fp32 scalar advanced by sgf_adam_tick, so CUDA-graph replays keep counting).
+ * SGF_ADAM_MAX_TENSORS, fp32 parameters / gradients / moments, hyper-parameters per tensor (its group's), one step count t per
+ * tensor on the device (fp32 scalars advanced by the call itself, so CUDA-graph replays keep counting and a parameter that had no
+ * gradient in some step keeps its own count, as in torch).
  *   g += wd*p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  * ------------------------------------------------------------------------------------------------ */
 #define SGF_ADAM_MAX_TENSORS 32
@@ -380,10 +403,9 @@ typedef struct {
     int64_t numel[SGF_ADAM_MAX_TENSORS];
     float lr[SGF_ADAM_MAX_TENSORS], beta1[SGF_ADAM_MAX_TENSORS], beta2[SGF_ADAM_MAX_TENSORS], eps[SGF_ADAM_MAX_TENSORS],
           weight_decay[SGF_ADAM_MAX_TENSORS];
-    const float* step;                          /* device fp32 scalar: t of THIS update (>= 1) */
+    float* step[SGF_ADAM_MAX_TENSORS];          /* device fp32 scalars: number of updates each tensor has received so far */
     int32_t chunk0[SGF_ADAM_MAX_TENSORS + 1];   /* filled by sgf_adam_step */
 } sgf_adam_args;
-int sgf_adam_tick(float* step /* device */, void* stream);      /* *step += 1 */
 int sgf_adam_step(sgf_adam_args* args /* host, chunk0 is written */, void* stream);
 
 #ifdef __cplusplus

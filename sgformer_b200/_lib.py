@@ -66,7 +66,7 @@ class AdamArgs(C.Structure):
         ("numel", _i64 * SGF_ADAM_MAX_TENSORS),
         ("lr", _f32 * SGF_ADAM_MAX_TENSORS), ("beta1", _f32 * SGF_ADAM_MAX_TENSORS), ("beta2", _f32 * SGF_ADAM_MAX_TENSORS),
         ("eps", _f32 * SGF_ADAM_MAX_TENSORS), ("weight_decay", _f32 * SGF_ADAM_MAX_TENSORS),
-        ("step", _vp),
+        ("step", _vp * SGF_ADAM_MAX_TENSORS),
         ("chunk0", _i32 * (SGF_ADAM_MAX_TENSORS + 1)),
     ]
 
@@ -98,6 +98,10 @@ _SIGS = {
     "sgf_add_self_loops": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sgf_subgraph": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_spmm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _i64, _vp]),
+    "sgf_spmm_flagged": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _i64, _vp, _i64, C.c_int, _vp]),
+    "sgf_signal": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "sgf_wait_flags": (C.c_int, [_vp, C.c_int, _vp]),
+    "sgf_csr_build_rot": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_spmm_heavy": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "sgf_gemm_nt": (C.c_int, [C.POINTER(GemmNtArgs), _vp]),
     "sgf_gemm_tn_ws_bytes": (C.c_int, [_i32, _i32, _i64, C.POINTER(_sz)]),
@@ -114,7 +118,6 @@ _SIGS = {
     "sgf_attn_gram_ws_floats": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_i64)]),
     "sgf_attn_gram_prepare_fwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
     "sgf_attn_gram_prepare_bwd": (C.c_int, [C.POINTER(AttnGramArgs), _vp]),
-    "sgf_adam_tick": (C.c_int, [_vp, _vp]),
     "sgf_adam_step": (C.c_int, [C.POINTER(AdamArgs), _vp]),
     "sgf_bn_finalize": (C.c_int, [_vp, _vp, _i64, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgf_bn_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int,

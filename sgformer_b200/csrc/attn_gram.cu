@@ -113,21 +113,24 @@ __global__ void __launch_bounds__(256) small_ops_kernel(const __grid_constant__ 
         }
 }
 
-// out[slot] += sum_{i<m, j<n} A(i,j) * B(i,j)   (one block per dot product; the slots are zeroed by the caller)
+// Frobenius inner products <A, B> = sum_{i<m, j<n} A(i,j) B(i,j): DOT_SPLIT blocks per product write their slice's sum to
+// part[d][blockIdx.y]; the scalar kernels add a slot's partials in fixed order (deterministic, no atomics).
+constexpr int DOT_SPLIT = 32;
 struct Dot {
     Mat A, B;
     int m, n;
-    float* out;
+    int slot;           // partial sums go to part[slot_part0 .. +DOT_SPLIT)
 };
 struct DotBatch {
     int n;
+    float* part;        // [n][DOT_SPLIT]
     Dot d[MAX_OPS];
 };
 __global__ void __launch_bounds__(256) dots_kernel(const __grid_constant__ DotBatch db) {
     const Dot& d = db.d[blockIdx.x];
     float s = 0.f;
     const int64_t total = (int64_t)d.m * d.n;
-    for (int64_t e = threadIdx.x; e < total; e += 256) {
+    for (int64_t e = (int64_t)blockIdx.y * 256 + threadIdx.x; e < total; e += 256 * DOT_SPLIT) {
         const int64_t i = e / d.n, j = e % d.n;
         s += d.A.p[i * d.A.rs + j * d.A.cs] * d.B.p[i * d.B.rs + j * d.B.cs];
     }
@@ -137,25 +140,38 @@ __global__ void __launch_bounds__(256) dots_kernel(const __grid_constant__ DotBa
     __syncthreads();
     if (threadIdx.x == 0) {
         float tsum = 0.f;
-        for (int w = 0; w < 8; ++w) tsum += red[w];     // fixed order: deterministic
-        atomicAdd(d.out, tsum);                          // the slot receives <= 2 terms, each from one block
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        db.part[blockIdx.x * DOT_SPLIT + blockIdx.y] = tsum;
     }
+}
+// sum of the partials of dot products [d0, d1) in fixed order
+__device__ __forceinline__ double dot_sum(const float* part, int d0, int d1) {
+    double t = 0.0;
+    for (int i = d0 * DOT_SPLIT; i < d1 * DOT_SPLIT; ++i) t += (double)part[i];
+    return t;
 }
 
 __global__ void init_sc_kernel(float* sc, float nf) {
     if (threadIdx.x < 16) sc[threadIdx.x] = threadIdx.x == SC_N ? nf : (threadIdx.x == SC_ONE ? 1.f : 0.f);
 }
-__global__ void scal_fwd_kernel(float* sc) {
+// forward dot products (in launch order): 0 <kx,Wk>  1 z1.bk  2 <qx,Wq>  3 q1.bq  4 bq.z1
+__global__ void scal_fwd_kernel(float* sc, const float* part) {
     // alpha = 1/(||q|| ||k||) in double: the two norms are sums over ~N*h terms
-    const double nq2 = (double)sc[SC_NQ2], nk2 = (double)sc[SC_NK2];
+    const double nk2 = dot_sum(part, 0, 2), nq2 = dot_sum(part, 2, 4);
+    sc[SC_NQ2] = (float)nq2;
+    sc[SC_NK2] = (float)nk2;
+    sc[SC_BQZ] = (float)dot_sum(part, 4, 5);
     const double alpha = 1.0 / (sqrt(nq2) * sqrt(nk2));
     const double beta = alpha / (double)sc[SC_N];
     sc[SC_ALPHA] = (float)alpha;
     sc[SC_BETA] = (float)beta;
     sc[SC_DEN] = (float)(beta * (double)sc[SC_BQZ] + 1.0);
 }
-__global__ void scal_bwd_kernel(float* sc) {
-    const double c = (double)sc[SC_BETA] * (double)sc[SC_IP];
+// backward dot products: 0 <dS,S>  1 dz.z1
+__global__ void scal_bwd_kernel(float* sc, const float* part) {
+    const double ip = dot_sum(part, 0, 2);
+    sc[SC_IP] = (float)ip;
+    const double c = (double)sc[SC_BETA] * ip;
     sc[SC_C] = (float)c;
     sc[SC_CQ] = (float)(-c / (double)sc[SC_NQ2]);
     sc[SC_CK] = (float)(-c / (double)sc[SC_NK2]);
@@ -193,10 +209,10 @@ static inline void rank1(Op& o, Coef c, const float* u, int64_t us, const float*
 }
 struct DotBuilder {
     DotBatch b;
-    DotBuilder() { memset(&b, 0, sizeof(b)); }
-    void add(Mat A, Mat B, int m, int n, float* out) { b.d[b.n++] = Dot{A, B, m, n, out}; }
+    explicit DotBuilder(float* part) { memset(&b, 0, sizeof(b)); b.part = part; }
+    void add(Mat A, Mat B, int m, int n) { b.d[b.n] = Dot{A, B, m, n, b.n}; ++b.n; }
     int launch(cudaStream_t st) {
-        dots_kernel<<<b.n, 256, 0, st>>>(b);
+        dots_kernel<<<dim3(b.n, DOT_SPLIT), 256, 0, st>>>(b);
         SGF_LAUNCH_CHECK(); count_launch();
         return SGF_OK;
     }
@@ -215,14 +231,19 @@ using namespace sgf::gram;
 
 extern "C" int sgf_attn_gram_ws_floats(int h, int m, int d, int64_t* n_floats) {
     if (!n_floats || h <= 0 || m <= 0 || d <= 0) return SGF_ERR_ARG;
-    *n_floats = (int64_t)m * d /* dS */ + m /* dz */ + (int64_t)m * h /* U */ + m /* t1 */ + d /* t2 */;
+    *n_floats = (int64_t)m * d /* dS */ + m /* dz */ + (int64_t)m * h /* U */ + m /* t1 */ + d /* t2 */ +
+                MAX_OPS * DOT_SPLIT /* dot-product partials */;
     return SGF_OK;
 }
 
 extern "C" int sgf_attn_gram_prepare_fwd(const sgf_attn_gram_args* a, void* stream) {
-    if (!args_ok(a)) return SGF_ERR_ARG;
+    if (!args_ok(a) || !a->ws) return SGF_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int h = a->h, m = a->m, d = a->d;
+    int64_t need = 0;
+    sgf_attn_gram_ws_floats(h, m, d, &need);
+    if (a->ws_floats < need) return SGF_ERR_ARG;
+    float* part = a->ws + (need - MAX_OPS * DOT_SPLIT);
     float* sc = a->sc;
     const float* scN = sc + SC_N;
     const float* beta = sc + SC_BETA;
@@ -243,15 +264,15 @@ extern "C" int sgf_attn_gram_prepare_fwd(const sgf_attn_gram_args* a, void* stre
         BatchBuilder bb;
         { Op& o = bb.add(m, d, a->S, d); prod1(o, cf(1.f), mat(a->kx, h), matT(a->wv, a->ld_wv), h); rank1(o, cf(1.f), a->z1, 1, a->bv, 1); }
         if ((rc = bb.launch(st))) return rc;
-        DotBuilder db;
-        db.add(mat(a->kx, h), mat(a->wk, a->ld_wk), m, h, sc + SC_NK2);
-        db.add(vec(a->z1), vec(a->bk), m, 1, sc + SC_NK2);
-        db.add(mat(a->qx, h), mat(a->wq, a->ld_wq), m, h, sc + SC_NQ2);
-        db.add(vec(a->q1), vec(a->bq), m, 1, sc + SC_NQ2);
-        db.add(vec(a->z1), vec(a->bq), m, 1, sc + SC_BQZ);
+        DotBuilder db(part);
+        db.add(mat(a->kx, h), mat(a->wk, a->ld_wk), m, h);
+        db.add(vec(a->z1), vec(a->bk), m, 1);
+        db.add(mat(a->qx, h), mat(a->wq, a->ld_wq), m, h);
+        db.add(vec(a->q1), vec(a->bq), m, 1);
+        db.add(vec(a->z1), vec(a->bq), m, 1);
         if ((rc = db.launch(st))) return rc;
     }
-    scal_fwd_kernel<<<1, 1, 0, st>>>(sc);
+    scal_fwd_kernel<<<1, 1, 0, st>>>(sc, part);
     SGF_LAUNCH_CHECK(); count_launch();
     {   // level 3: operands of the apply GEMM
         BatchBuilder bb;
@@ -279,10 +300,10 @@ extern "C" int sgf_attn_gram_prepare_bwd(const sgf_attn_gram_args* a, void* stre
     float* U = dz + m;
     float* t1 = U + (int64_t)m * h;
     float* t2 = t1 + m;
+    float* part = a->ws + (need - MAX_OPS * DOT_SPLIT);
     const int64_t ldc = d + h;       // pitch of bcat = [Bt^T | A3]
     float* A3 = a->bcat + d;
     int rc;
-    SGF_CUDA_TRY(cudaMemsetAsync(sc + SC_IP, 0, sizeof(float), st));
     {   // level 1: dS, dz; the Bt^T half of the dx operand
         BatchBuilder bb;
         { Op& o = bb.add(m, d, dS, d); prod1(o, cf(1.f), mat(a->wq, a->ld_wq), mat(a->P, d), h); rank1(o, cf(1.f), a->bq, 1, a->cs, 1); }
@@ -291,11 +312,11 @@ extern "C" int sgf_attn_gram_prepare_bwd(const sgf_attn_gram_args* a, void* stre
         if ((rc = bb.launch(st))) return rc;
     }
     {   // level 2: c = beta (<dS,S> + <dz,z1>);  U = dS Wv, t1 = dS bv + dz, t2 = dS^T bk
-        DotBuilder db;
-        db.add(mat(dS, d), mat(a->S, d), m, d, sc + SC_IP);
-        db.add(vec(dz), vec(a->z1), m, 1, sc + SC_IP);
+        DotBuilder db(part);
+        db.add(mat(dS, d), mat(a->S, d), m, d);
+        db.add(vec(dz), vec(a->z1), m, 1);
         if ((rc = db.launch(st))) return rc;
-        scal_bwd_kernel<<<1, 1, 0, st>>>(sc);
+        scal_bwd_kernel<<<1, 1, 0, st>>>(sc, part);
         SGF_LAUNCH_CHECK(); count_launch();
         BatchBuilder bb;
         { Op& o = bb.add(m, h, U, h); prod1(o, cf(1.f), mat(dS, d), mat(a->wv, a->ld_wv), d); }

@@ -140,6 +140,18 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* 
     }
 }
 
+// Row-sharded runs with pushed operand blocks (sgf_spmm_flagged): column ids are stored ROTATED, col' = (col - rot) mod `mod`, so
+// that the rank's own row block comes first in every row and the gathered operand buffer is indexed by arrival slot.
+__global__ void csr_rotate_cols_kernel(int32_t* __restrict__ col, const int64_t* __restrict__ rowptr, int64_t n, int64_t rot, int64_t mod) {
+    const int64_t total = rowptr[n];
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t v = (int64_t)col[i] - rot;
+        if (v < 0) v += mod;
+        col[i] = (int32_t)v;
+    }
+}
+
 __global__ void csr_add_loops_kernel(int64_t n, int64_t row_begin, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
                                      int32_t* __restrict__ col) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -533,10 +545,18 @@ extern "C" int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
 extern "C" int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
                                   int by_source, int self_loop_mode, int64_t* rowptr, int32_t* col, float* dinv, void* ws,
                                   size_t ws_bytes, void* stream) {
+    return sgf_csr_build_rot(edge_index, nnz, row_begin, row_end, n_cols, by_source, self_loop_mode, 0, 0, rowptr, col, dinv, ws,
+                             ws_bytes, stream);
+}
+
+extern "C" int sgf_csr_build_rot(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
+                                 int by_source, int self_loop_mode, int64_t col_rot, int64_t col_mod, int64_t* rowptr, int32_t* col,
+                                 float* dinv, void* ws, size_t ws_bytes, void* stream) {
     const int64_t n = row_end - row_begin;
     if (nnz < 0 || n < 0 || row_begin < 0 || row_end > n_cols || n_cols >= (int64_t)INT32_MAX || !rowptr ||
         (!col && nnz + n > 0) || !ws)
         return SGF_ERR_ARG;
+    if (col_mod != 0 && (col_mod < n_cols || col_mod >= (int64_t)INT32_MAX || col_rot < 0 || col_rot >= col_mod)) return SGF_ERR_ARG;
     if (nnz > 0 && !edge_index) return SGF_ERR_ARG;
     if (self_loop_mode != 0 && self_loop_mode != 1) return SGF_ERR_ARG;
     CsrWs w = carve_ws(ws, nnz, n);
@@ -561,6 +581,10 @@ extern "C" int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_
         SGF_LAUNCH_CHECK(); count_launch();
     }
     if (n > 0) {
+        if (col_mod > 0 && nnz + n > 0) {
+            csr_rotate_cols_kernel<<<grid_for(nnz + n, 256), 256, 0, st>>>(col, rowptr, n, col_rot, col_mod);
+            SGF_LAUNCH_CHECK(); count_launch();
+        }
         int rcs = sort_rows(rowptr, col, n, w, st);
         if (rcs) return rcs;
         if (dinv) {

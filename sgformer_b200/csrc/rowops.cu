@@ -350,12 +350,12 @@ __global__ void __launch_bounds__(kRowBlock, 3) ln_bwd_kernel(const T* __restric
 // and the column sums cs = sum_r gnum'[r,:], pg = sum_r xa[r,:]*gden'[r], sg = sum_r gden'[r] that the h x h backward algebra
 // needs (sgf_attn_gram_prepare_bwd) accumulate in registers like dgamma / dbeta.  xa = the attention layer's input (== r when
 // the layer has a residual connection: then it is not loaded twice).
-template <typename T, int CPL, bool DROP>
-__global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_kernel(const T* __restrict__ dy, const T* __restrict__ o, const T* __restrict__ rr,
+template <typename T, int CPL, bool DROP, bool RELU, int MINB>
+__global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : MINB)) ln_bwd_attn_kernel(const T* __restrict__ dy, const T* __restrict__ o, const T* __restrict__ rr,
                                                                     const T* __restrict__ xa, int64_t ld, int64_t rows, int h, int chunks,
                                                                     int lpr_log2, float a, float b, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, const float* __restrict__ stats,
-                                                                    int use_ln, int use_relu, float p, uint64_t seed, float gscale,
+                                                                    int use_ln, float p, uint64_t seed, float gscale,
                                                                     const float* __restrict__ den, T* __restrict__ gnum,
                                                                     float* __restrict__ gden, T* __restrict__ dr,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -363,9 +363,10 @@ __global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_ker
     constexpr int VN = Vec16<T>::N;
     extern __shared__ float sm[];
     Lane<T, CPL> L(chunks, lpr_log2);
-    float g[CPL][VN], be[CPL][VN], dg[CPL][VN], db[CPL][VN], acs[CPL][VN], apg[CPL][VN];
+    // register budget (85 at 3 CTAs/SM): gamma + four column accumulators live across the row loop; beta only exists in the
+    // RELU instantiation (the mask needs the LayerNorm output); o and the layer input stay packed until they are used
+    float g[CPL][VN], dg[CPL][VN], db[CPL][VN], acs[CPL][VN], apg[CPL][VN];
     L.load_vec(use_ln ? gamma : nullptr, g, 1.f);
-    L.load_vec(use_ln ? beta : nullptr, be, 0.f);
     SGF_ZERO(dg) SGF_ZERO(db) SGF_ZERO(acs) SGF_ZERO(apg)
     float asg = 0.f;
     const float inv_h = 1.f / (float)h;
@@ -387,19 +388,26 @@ __global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_ker
     for (int64_t rb = L.row0 - L.grp; rb < rows; rb += L.row_step) {
         const int64_t r = rb + L.grp;
         const bool live = r < rows;
-        float ov[CPL][VN], u[CPL][VN], gy[CPL][VN], t[CPL][VN];
+        float u[CPL][VN], gy[CPL][VN];
+        uint4 co[CPL], cr[CPL];          // packed copies of this row's o and residual (4 registers per chunk)
         const float mean = nmean, rstd = nrstd, inv_den = ninv;
-        L.unpack(nx, ov);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) { co[c] = nx[c]; cr[c] = nr[c]; }
+        L.unpack(nx, u);
         L.unpack(ng, gy);
         if (rr) {
-            L.unpack(nr, t);
-            SGF_FOR_ELEMS u[c][i] = a * ov[c][i] + b * t[c][i];
+            float t[CPL][VN];
+            L.unpack(cr, t);
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i] + b * t[c][i];
         } else {
-            SGF_FOR_ELEMS { u[c][i] = a * ov[c][i]; t[c][i] = 0.f; }
+            SGF_FOR_ELEMS u[c][i] = a * u[c][i];
         }
         if (!xa_is_r) {
-            if (live) L.load(xa, ld, r, t);
-            else SGF_ZERO(t)
+            if (live) L.load_raw(xa, ld, r, cr);
+            else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) cr[c] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         {
             const int64_t rn = r + L.row_step;
@@ -417,13 +425,16 @@ __global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_ker
         }
         SGF_FOR_ELEMS gy[c][i] *= gscale;
         if (DROP) L.dropout(gy, seed, r, chunks, thr16, inv_keep);
-        float du[CPL][VN];
+        // du (gradient w.r.t. u = a*o + b*r) overwrites gy
         if (use_ln) {
             float s1 = 0.f, s2 = 0.f;
             SGF_FOR_ELEMS {
-                float xh = L.cval[c] ? (u[c][i] - mean) * rstd : 0.f;
-                float pre = xh * g[c][i] + be[c][i];
-                float gg = (use_relu && pre <= 0.f) ? 0.f : gy[c][i];
+                const float xh = L.cval[c] ? (u[c][i] - mean) * rstd : 0.f;
+                float gg = gy[c][i];
+                if (RELU) {
+                    const float be = L.cval[c] ? beta[L.coff[c] + i] : 0.f;
+                    if (xh * g[c][i] + be <= 0.f) gg = 0.f;
+                }
                 dg[c][i] += gg * xh;
                 db[c][i] += gg;
                 gg *= g[c][i];
@@ -434,24 +445,26 @@ __global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : 2)) ln_bwd_attn_ker
             }
             s1 = L.row_sum(s1) * inv_h;
             s2 = L.row_sum(s2) * inv_h;
-            SGF_FOR_ELEMS du[c][i] = rstd * (gy[c][i] - s1 - u[c][i] * s2);
-        } else {
-            SGF_FOR_ELEMS du[c][i] = (use_relu && u[c][i] <= 0.f) ? 0.f : gy[c][i];
+            SGF_FOR_ELEMS gy[c][i] = rstd * (gy[c][i] - s1 - u[c][i] * s2);
+        } else if (RELU) {
+            SGF_FOR_ELEMS if (u[c][i] <= 0.f) gy[c][i] = 0.f;
+        }
+        if (live && dr) {
+            SGF_FOR_ELEMS u[c][i] = b * gy[c][i];
+            L.store(dr, ld, r, u);
         }
         // attention-backward prologue on ga = a*du
+        L.unpack(co, u);                 // o again
         float dot = 0.f;
-        SGF_FOR_ELEMS { const float ga = L.cval[c] ? a * du[c][i] : 0.f; dot += ga * ov[c][i]; gy[c][i] = ga * inv_den; }
+        SGF_FOR_ELEMS { const float ga = L.cval[c] ? a * gy[c][i] : 0.f; dot += ga * u[c][i]; gy[c][i] = ga * inv_den; }
         dot = L.row_sum(dot);
         const float gd = live ? -dot * inv_den : 0.f;
-        SGF_FOR_ELEMS { acs[c][i] += gy[c][i]; apg[c][i] += t[c][i] * gd; }
+        L.unpack(cr, u);                 // the layer input
+        SGF_FOR_ELEMS { acs[c][i] += gy[c][i]; apg[c][i] += u[c][i] * gd; }
         if (L.sub == 0) asg += gd;
         if (live) {
             L.store(gnum, ld, r, gy);
             if (L.sub == 0) gden[r] = gd;
-            if (dr) {
-                SGF_FOR_ELEMS gy[c][i] = b * du[c][i];
-                L.store(dr, ld, r, gy);
-            }
         }
     }
     if (use_ln && dgamma) flush_columns<T, CPL>(L, dg, sm, h, dgamma);
@@ -1090,10 +1103,24 @@ extern "C" int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, con
     if (use_ln && (!gamma || !beta || !stats)) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
-                                         (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,
-                                         gamma, beta, stats, use_ln, use_relu, p, seed, gscale, den, (T*)gnum, gden, (T*)dr, dgamma,
-                                         dbeta, cs, pg, sg)));
+    // resident CTAs per SM for the one-chunk-per-lane geometry: 3 (80 registers, ~20 spilled to L1) or 2 (no spills); A/B on the GPU
+    static const int minb = [] { const char* e = getenv("SGF_LNATTN_BLOCKS"); return (e && e[0] == '2') ? 2 : 3; }();
+    if (minb == 2 && !use_relu) {
+        SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP, false, 2><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                             (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,
+                                             gamma, beta, stats, use_ln, p, seed, gscale, den, (T*)gnum, gden, (T*)dr, dgamma,
+                                             dbeta, cs, pg, sg)));
+    } else if (use_relu) {
+        SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP, true, 3><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                             (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,
+                                             gamma, beta, stats, use_ln, p, seed, gscale, den, (T*)gnum, gden, (T*)dr, dgamma,
+                                             dbeta, cs, pg, sg)));
+    } else {
+        SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP, false, 3><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
+                                             (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,
+                                             gamma, beta, stats, use_ln, p, seed, gscale, den, (T*)gnum, gden, (T*)dr, dgamma,
+                                             dbeta, cs, pg, sg)));
+    }
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

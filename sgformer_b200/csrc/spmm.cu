@@ -38,7 +38,7 @@ constexpr int kUnroll = SGF_SPMM_UNROLL;
 constexpr int kMinBlocks = SGF_SPMM_MIN_BLOCKS;
 
 // gather-accumulate up to 32 neighbour rows whose ids sit one per lane in my_idx (cnt valid), all lane groups cooperating
-template <typename T, int CPL>
+template <typename T, int CPL, bool COH = false>
 __device__ __forceinline__ void gather_item(int my_idx, int cnt, const T* __restrict__ x, int64_t ldx, int groups, int grp,
                                             const int (&coff)[CPL], const bool (&cval)[CPL], float (&acc)[CPL][Vec16<T>::N]) {
     constexpr int VN = Vec16<T>::N;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void gather_item(int my_idx, int cnt, const T* __rest
             const T* src = x + (int64_t)(nb[u] < 0 ? 0 : nb[u]) * ldx;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                if (nb[u] >= 0 && cval[c]) v[u][c] = ldg_nc_na(src + coff[c]);
+                if (nb[u] >= 0 && cval[c]) v[u][c] = COH ? ldg_na(src + coff[c]) : ldg_nc_na(src + coff[c]);
                 else v[u][c] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
@@ -84,16 +84,71 @@ __device__ __forceinline__ void gather_range(const int32_t* __restrict__ col, co
     }
 }
 
+// ---- row-sharded runs: operand blocks pushed by the peers while the kernel runs ------------------------------------------------
+// x is the gathered operand [n_slots * slot_rows, h]: slot 0 = this rank's own rows (present), slot s > 0 = the rows of rank
+// (rank + s) mod world, written by that rank's copy engine over NVLink; flags[s] != 0 once slot s has landed (set by the sender
+// after its copy, sgf_signal).  Column ids are rotated (sgf_csr_build_rot), rows sorted by them, so a row's neighbours are met in
+// slot order: a warp waits for a slot the first time one of its 32 current column ids falls into it.  One warp per CTA polls the
+// global flags (acquire.sys); the others watch the CTA's shared `ready` counter.  Bounded spin: a protocol error traps.
+struct SlotWait {
+    const uint32_t* flags;
+    int64_t slot_rows;
+    int n_slots;
+};
+__device__ __forceinline__ int wait_slots(int need, volatile int* s_ready, int* s_lock, const uint32_t* flags) {
+    uint32_t spins = 0;
+    while (true) {
+        const int r = *s_ready;
+        if (r >= need) { __threadfence_block(); return r; }
+        if (atomicCAS(s_lock, 0, 1) == 0) {             // this warp polls for the CTA
+            int got = *s_ready;
+            while (got < need && ld_acquire_sys_u32(flags + got + 1) != 0u) ++got;
+            if (got > r) atomicMax(const_cast<int*>(s_ready), got);
+            __threadfence_block();
+            atomicExch(s_lock, 0);
+            if (got >= need) return got;
+            __nanosleep(400);
+        } else {
+            __nanosleep(200);
+        }
+        if (++spins > (1u << 24)) __trap();             // ~ seconds: the peers never delivered
+    }
+}
+template <typename T, int CPL>
+__device__ __forceinline__ void gather_range_flagged(const int32_t* __restrict__ col, const T* __restrict__ x, int64_t ldx, int64_t s,
+                                                     int64_t e, int lane, int groups, int grp, const int (&coff)[CPL],
+                                                     const bool (&cval)[CPL], float (&acc)[CPL][Vec16<T>::N], const SlotWait& sw,
+                                                     int& ready, volatile int* s_ready, int* s_lock) {
+    for (int64_t base = s; base < e; base += 32) {
+        const int cnt = (int)((e - base) < 32 ? (e - base) : 32);
+        const int my_idx = lane < cnt ? ldg_nc_na_s32(col + base + lane) : -1;
+        const int slot = my_idx >= 0 ? (int)(my_idx / sw.slot_rows) : 0;
+        const int need = __reduce_max_sync(0xffffffffu, slot);
+        if (need > ready) {
+            int got = 0;
+            if (lane == 0) got = wait_slots(need < sw.n_slots ? need : sw.n_slots - 1, s_ready, s_lock, sw.flags);
+            ready = __shfl_sync(0xffffffffu, got, 0);
+        }
+        gather_item<T, CPL, true>(my_idx, cnt, x, ldx, groups, grp, coff, cval, acc);
+    }
+}
+
 // One warp per output row, rows r = warp, warp + nwarps, ...; rows longer than max_len (> 0) are left to the segmented path
 // below.  SGF_SPMM_PIPELINE=1 software-pipelines the dependent chain rowptr -> column ids -> feature rows across the warp's work
 // items (an item = up to 32 neighbours of one row): while the gathers of item i are in flight, the column ids of item i+1 (same
 // row or the warp's next row) and the rowptr entries of the row after next are already loading (slower on B200, see above).
-template <typename T, int CPL>
+template <typename T, int CPL, bool FLAGS = false>
 __global__ void __launch_bounds__(kSpmmBlock, kMinBlocks)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
                  const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2,
-                 int64_t max_len) {
+                 int64_t max_len, SlotWait sw) {
     constexpr int VN = Vec16<T>::N;
+    __shared__ int s_ready, s_lock;
+    int ready = 0;
+    if (FLAGS) {
+        if (threadIdx.x == 0) { s_ready = 0; s_lock = 0; }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int lpr = 1 << lpr_log2;
     const int groups = 32 >> lpr_log2;
@@ -110,6 +165,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
         coff[c] = ch * VN;
     }
 #if SGF_SPMM_PIPELINE
+    static_assert(!FLAGS, "the flagged variant uses the simple loop");
     int64_t r = warp0;
     if (r >= n_rows) return;
     // current row [s, e) (a skipped hub row behaves like an empty row that is not stored), next row [sn, en)
@@ -185,7 +241,8 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
         for (int c = 0; c < CPL; ++c)
 #pragma unroll
             for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
-        gather_range<T, CPL>(col, x, ldx, s, e, lane, groups, grp, coff, cval, acc);
+        if (FLAGS) gather_range_flagged<T, CPL>(col, x, ldx, s, e, lane, groups, grp, coff, cval, acc, sw, ready, &s_ready, &s_lock);
+        else gather_range<T, CPL>(col, x, ldx, s, e, lane, groups, grp, coff, cval, acc);
         for (int o = lpr; o < 32; o <<= 1) {
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
@@ -273,7 +330,7 @@ __global__ void spmm_heavy_finalize_kernel(const float* __restrict__ partial, co
 
 template <typename T>
 static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
-                       void* y, int64_t ldy, int64_t n_rows, int h, int64_t max_len, cudaStream_t st) {
+                       void* y, int64_t ldy, int64_t n_rows, int h, int64_t max_len, cudaStream_t st, const SlotWait* slots = nullptr) {
     constexpr int VN = Vec16<T>::N;
     if (h % VN != 0 || ldx % VN != 0 || ldy % VN != 0) return SGF_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return SGF_ERR_ARG;
@@ -287,12 +344,21 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* r
     int64_t blocks = (warps_needed * 32 + kSpmmBlock - 1) / kSpmmBlock;
     int64_t cap = (int64_t)num_sms() * kMinBlocks * 8;  // 8 waves of the resident CTAs per SM, grid-stride beyond
     if (blocks > cap) blocks = cap;
+    // flagged variant: ONE wave of resident CTAs (grid-stride over the rows).  Its CTAs may spin on operand blocks that have not
+    // arrived; with no CTA queued behind them the SMs keep room for the 1-thread signal kernels of this GPU's own pushes
+    // (another stream), so two GPUs can never wait on each other's signals.
+    if (slots && blocks > (int64_t)num_sms() * kMinBlocks) blocks = (int64_t)num_sms() * kMinBlocks;
     const T* xp = static_cast<const T*>(x);
     T* yp = static_cast<T*>(y);
+    const SlotWait sw = slots ? *slots : SlotWait{nullptr, 1, 1};
 #define SGF_SPMM_CASE(N)                                                                                              \
     case N:                                                                                                           \
-        spmm_rows_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy,      \
-                                                                        n_rows, chunks, lpr_log2, max_len);            \
+        if (slots)                                                                                                    \
+            spmm_rows_kernel<T, N, true><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy, \
+                                                                                  n_rows, chunks, lpr_log2, max_len, sw);   \
+        else                                                                                                          \
+            spmm_rows_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy,  \
+                                                                            n_rows, chunks, lpr_log2, max_len, sw);    \
         break;
     switch (cpl) {
         SGF_SPMM_CASE(1)
@@ -346,7 +412,44 @@ static int launch_heavy(const int32_t* col, const float* row_scale, const void* 
     return SGF_OK;
 }
 
+__global__ void signal_kernel(uint32_t* flag, uint32_t value) { st_release_sys_u32(flag, value); }
+__global__ void wait_flags_kernel(const uint32_t* flags, int n) {
+    uint32_t spins = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        while (ld_acquire_sys_u32(flags + i) == 0u) {
+            __nanosleep(500);
+            if (++spins > (1u << 24)) __trap();
+        }
+}
+
 }  // namespace sgf
+
+extern "C" int sgf_spmm_flagged(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
+                                void* y, int64_t ldy, int64_t n_rows, int h, int dtype, int64_t max_row_len, const uint32_t* flags,
+                                int64_t slot_rows, int n_slots, void* stream) {
+    if (!rowptr || n_rows < 0 || h <= 0 || (n_rows > 0 && (!x || !y)) || max_row_len < 0 || !flags || slot_rows <= 0 || n_slots < 1)
+        return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const sgf::SlotWait sw{flags, slot_rows, n_slots};
+    if (dtype == 0) return sgf::launch_spmm<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st, &sw);
+    if (dtype == 1) return sgf::launch_spmm<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st, &sw);
+    return SGF_ERR_ARG;
+}
+
+extern "C" int sgf_signal(uint32_t* flag, uint32_t value, void* stream) {
+    if (!flag) return SGF_ERR_ARG;
+    sgf::signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    SGF_LAUNCH_CHECK(); sgf::count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_wait_flags(const uint32_t* flags, int n, void* stream) {
+    if (!flags || n < 0) return SGF_ERR_ARG;
+    if (n == 0) return SGF_OK;
+    sgf::wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n);
+    SGF_LAUNCH_CHECK(); sgf::count_launch();
+    return SGF_OK;
+}
 
 extern "C" int sgf_spmm(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx,
                         void* y, int64_t ldy, int64_t n_rows, int h, int dtype, int64_t max_row_len, void* stream) {

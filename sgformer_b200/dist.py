@@ -1,14 +1,28 @@
 """Row-sharded execution across GPUs: nodes are split into contiguous row blocks, parameters are
 replicated, and the schedule exchanges only
 
-  C1  {S' = k^T v, z' = k^T 1, ||q||^2, ||k||^2}      one all-reduce per attention layer (h x h + 3h floats)
-  C2  {dS', dz'}                                        its backward
+  C1  {G = x^T x, s = x^T 1} (Gram-form attention; {S', z', ||q||^2, ||k||^2} on the multi-head path)   one all-reduce per layer
+  C2  {P = x^T gnum', x^T gden', column sums} (resp. {dS', dz'})                                          its backward
   C3  BatchNorm column sums (forward and backward)      2h floats each
-  C4  the pre-scaled SpMM operand rows                  all-gather of [N/P, h] blocks (on the reference's graphs nearly
-                                                        every remote row is a halo row, so the halo IS the all-gather)
+  C4  the pre-scaled SpMM operand rows                  every rank needs the operand rows its CSR block references
   C5  parameter gradients                               one flattened all-reduce per step
 
-through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  `Comm(None)` is the single-GPU no-op."""
+through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  `Comm(None)` is the single-GPU no-op.
+
+C4 — the halo exchange.  On the reference's graphs (uniform random, mean degree 40-50, P <= 8 row blocks) every remote row is
+referenced by some local row, so the halo of a rank IS the other ranks' blocks; what can be won is overlap, not volume.  Three modes
+(`SGF_C4_MODE`, default `push` on CUDA when symmetric memory can be set up, else `allgather`):
+
+  push       fused compute + exchange.  Every rank owns a symmetric buffer [world*block, h] per SpMM of the step.  The producer of the
+             operand writes its block straight into slot 0; the rank then PUSHES the block into slot (rank - r) mod world of every peer
+             r with copy-engine peer copies over NVLink (a side stream: no SMs, no NCCL kernels) and raises the peer's arrival flag.
+             The SpMM (`sgf_spmm_flagged`) starts immediately on the local slot: the CSR shard stores ROTATED column ids
+             (`sgf_csr_build_rot`), so every row meets its neighbours in arrival order and a warp waits only when it reaches a slot
+             whose flag is still down.  The consumer lowers its flags after the SpMM; the step's collectives (C1 / C5) order the reuse
+             of a buffer between steps.
+  rotated    the same rotated layout filled by one all-gather (CPU tests of the layout; no overlap).
+  allgather  r1 behaviour: blocking all-gather of the blocks in rank order, plain SpMM.
+"""
 from __future__ import annotations
 
 import os
@@ -19,11 +33,13 @@ import torch.distributed as dist
 
 Tensor = torch.Tensor
 
-# Column chunks of the C4 all-gather / SpMM pipeline (1 = one blocking all-gather per SpMM).  Measured on 2 B200s at the
-# products shape (profiles/r1_scaling.md): 60.1 ms/step with 1 chunk, 61.2 with 2, 61.3 with 4 - NCCL's all-gather kernels need SMs
-# that the HBM-bound SpMM grid already fills, so the transfer is not hidden and the narrower SpMMs cost more; default stays 1.
+# Column chunks of the all-gather / SpMM pipeline of the `allgather` mode (1 = one blocking all-gather per SpMM).  Measured on
+# 2 B200s at the products shape (profiles/r1_scaling.md): 60.1 ms/step with 1 chunk, 61.2 with 2, 61.3 with 4 - NCCL's all-gather
+# kernels need SMs that the HBM-bound SpMM grid already fills; hence the copy-engine `push` mode.
 C4_CHUNKS = int(os.environ.get("SGF_C4_CHUNKS", "1"))
 C4_MIN_CHUNK_BYTES = 256      # gathered rows stay >= two full 128-byte lines per neighbour
+C4_MODE = os.environ.get("SGF_C4_MODE", "auto")
+MAX_PUSH_BUFFERS = 16         # SpMMs per step that get their own symmetric buffer (2 * GNN layers)
 
 
 def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -33,8 +49,36 @@ def partition(n: int, world: int, rank: int) -> Tuple[int, int]:
     return r0, min(n, r0 + block)
 
 
+class _PushState:
+    """Symmetric operand buffers + arrival flags of the `push` mode (one set per (h, dtype))."""
+
+    def __init__(self, comm: "Comm", h: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.comm, self.h, self.dtype, self.device = comm, h, dtype, device
+        self.group = comm.group if comm.group is not None else dist.group.WORLD
+        self.bufs = {}                       # k -> (local [world*block, h], [peer views of their buffers])
+        w = comm.world
+        self.flags = symm.empty((MAX_PUSH_BUFFERS, w), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        hdl = symm.rendezvous(self.flags, self.group)
+        self.peer_flags = [hdl.get_buffer(r, (MAX_PUSH_BUFFERS, w), torch.int32) for r in range(w)]
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)       # every rank's flags are zero before anybody signals
+
+    def buffer(self, k: int):
+        if k not in self.bufs:
+            w, b = self.comm.world, self.comm.block
+            t = self.symm.empty((w * b, self.h), dtype=self.dtype, device=self.device)
+            hdl = self.symm.rendezvous(t, self.group)          # collective: the schedule reaches it in the same order on all ranks
+            peers = [hdl.get_buffer(r, (w * b, self.h), self.dtype) for r in range(w)]
+            self.bufs[k] = (t, peers)
+        return self.bufs[k]
+
+
 class Comm:
-    def __init__(self, group=None, n_global: Optional[int] = None):
+    def __init__(self, group=None, n_global: Optional[int] = None, c4_mode: Optional[str] = None):
         self.group = group
         self.active = group is not None or (dist.is_available() and dist.is_initialized() and n_global is not None)
         if self.active:
@@ -47,6 +91,28 @@ class Comm:
             raise ValueError("Comm needs the global node count")
         self.block = (n_global + self.world - 1) // self.world if n_global is not None else None
         self.rows = partition(n_global, self.world, self.rank) if n_global is not None else None
+        mode = c4_mode or C4_MODE
+        if mode == "auto":
+            mode = "push" if (self.active and self.world > 1 and dist.get_backend(group) == "nccl") else "allgather"
+        if not self.active or self.world == 1:
+            mode = "allgather"
+        if mode not in ("push", "rotated", "allgather"):
+            raise ValueError(f"unknown C4 mode {mode!r}")
+        self.c4_mode = mode
+        self._push = {}            # (h, dtype) -> _PushState
+        self._spmm_calls = 0       # position of the next SpMM inside the current step (selects the symmetric buffer)
+        self._push_failed = False
+
+    # column-id rotation the CSR shard of this rank must be built with (None: global ids)
+    @property
+    def col_rot(self) -> Optional[Tuple[int, int]]:
+        if self.c4_mode in ("push", "rotated") and self.active and self.world > 1:
+            return (self.rank * self.block, self.world * self.block)
+        return None
+
+    def begin_step(self):
+        """Called at the start of every sharded forward: SpMM k of this step uses symmetric buffer k."""
+        self._spmm_calls = 0
 
     # -- small reductions (C1, C2, C3, C5) ----------------------------------------------------------
     def allreduce_(self, *tensors: Tensor):
@@ -81,7 +147,7 @@ class Comm:
         return out[:self.n_global]
 
     def c4_chunks(self, h: int, elem_size: int) -> int:
-        """Column chunks of the C4 pipeline (C4_CHUNKS, reduced until the chunk rows are >= C4_MIN_CHUNK_BYTES)."""
+        """Column chunks of the all-gather pipeline (C4_CHUNKS, reduced until the chunk rows are >= C4_MIN_CHUNK_BYTES)."""
         if not self.active or self.world == 1:
             return 1
         want = C4_CHUNKS
@@ -89,16 +155,55 @@ class Comm:
             want -= 1
         return want
 
-    def spmm_gathered(self, spmm, rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x_local: Tensor, heavy=None) -> Tensor:
-        """C4 + SpMM: y[rows of this rank] = scale * A[rows, :] @ all_gather(x_local).
+    def _push_state(self, h: int, dtype, device) -> Optional[_PushState]:
+        key = (h, dtype)
+        if key not in self._push and not self._push_failed:
+            try:
+                self._push[key] = _PushState(self, h, dtype, device)
+            except Exception as exc:      # no symmetric memory on this system: every rank takes the all-gather route
+                import warnings
+                warnings.warn(f"sgformer_b200: symmetric memory unavailable ({type(exc).__name__}: {exc}); C4 falls back to "
+                              f"the rotated all-gather (no overlap)")
+                self._push_failed = True
+        return self._push.get(key)
 
-        The operand is exchanged in column chunks, each an asynchronous all-gather on NCCL's stream; the SpMM of chunk c
-        (`spmm(rowptr, col, row_scale, x_chunk, out=y[:, chunk], heavy=...)`, i.e. kernels.spmm) starts as soon as chunk c
-        has arrived and overlaps the transfer of chunk c+1.  On uniform random graphs every remote row is a halo row, so
-        the exchange cannot be smaller than the all-gather; it can only be hidden."""
+    def operand_out(self, n_local: int, h: int, dtype, device) -> Optional[Tensor]:
+        """Where the producer of the NEXT SpMM operand should write its [n_local, h] block so that it needs no staging copy:
+        slot 0 of that SpMM's symmetric buffer (push mode), else None (the caller allocates)."""
+        esize = 2 if dtype == torch.bfloat16 else 4
+        if self.c4_mode != "push" or not self.active or self.world == 1 or (h * esize) % 16 != 0 or device.type != "cuda":
+            return None
+        st = self._push_state(h, dtype, device)
+        if st is None or self._spmm_calls >= MAX_PUSH_BUFFERS:
+            return None
+        buf, _ = st.buffer(self._spmm_calls)
+        return buf[:n_local]
+
+    def _rotated_gather(self, x_local: Tensor) -> Tensor:
+        """all-gather into the rotated slot order (slot s = block of rank (rank + s) mod world)."""
+        full = self.allgather_rows(x_local)
+        w, b = self.world, self.block
+        if full.shape[0] != w * b:
+            pad = torch.zeros((w * b, full.shape[1]), dtype=full.dtype, device=full.device)
+            pad[:full.shape[0]] = full
+            full = pad
+        return torch.roll(full, shifts=-self.rank * b, dims=0)
+
+    def spmm_gathered(self, spmm, rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x_local: Tensor, heavy=None) -> Tensor:
+        """C4 + SpMM: y[rows of this rank] = scale * A[rows, :] @ (operand rows of every rank), `spmm` = kernels.spmm.
+        The CSR shard must have been built with this Comm's `col_rot`."""
         if not self.active or self.world == 1:
             return spmm(rowptr, col, row_scale, x_local, heavy=heavy)
+        k = self._spmm_calls
+        self._spmm_calls += 1
         n_loc, h = x_local.shape
+        if self.c4_mode == "push":
+            st = self._push_state(h, x_local.dtype, x_local.device) if k < MAX_PUSH_BUFFERS else None
+            if st is not None and x_local.is_cuda:
+                return self._spmm_pushed(st, k, rowptr, col, row_scale, x_local, heavy)
+            return spmm(rowptr, col, row_scale, self._rotated_gather(x_local), heavy=heavy)
+        if self.c4_mode == "rotated":
+            return spmm(rowptr, col, row_scale, self._rotated_gather(x_local), heavy=heavy)
         nch = self.c4_chunks(h, x_local.element_size())
         if nch == 1:
             return spmm(rowptr, col, row_scale, self.allgather_rows(x_local), heavy=heavy)
@@ -118,6 +223,33 @@ class Comm:
             work.wait()
             spmm(rowptr, col, row_scale, gc[:self.n_global], out=out[:, c * hc:(c + 1) * hc], heavy=heavy)
         return out
+
+    def _spmm_pushed(self, st: _PushState, k: int, rowptr, col, row_scale, x_local: Tensor, heavy) -> Tensor:
+        from . import kernels as K
+        w, b, rank = self.world, self.block, self.rank
+        buf, peers = st.buffer(k)
+        n_loc = x_local.shape[0]
+        own = buf[:n_loc]
+        if x_local.data_ptr() != own.data_ptr():
+            own.copy_(x_local)                       # the producer did not write in place (operand_out was not used)
+        main = torch.cuda.current_stream(st.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(st.side):
+            st.side.wait_event(ready)
+            for s in range(1, w):                    # my block is slot s of rank (rank - s): nearest consumer position first
+                r = (rank - s) % w
+                peers[r][s * b:s * b + n_loc].copy_(own, non_blocking=True)      # copy-engine peer copy over NVLink
+                K.signal(st.peer_flags[r][k, s:s + 1], 1)
+            done = torch.cuda.Event()
+            done.record(st.side)
+        y = K.spmm_flagged(rowptr, col, row_scale, buf, st.flags[k], b, heavy=heavy)
+        # every peer's signal of THIS use has been seen before the flags are lowered for the next step (a slot no row references
+        # would otherwise leave a late signal behind); the step's collectives (C1 / C5) order the reuse of the buffer itself
+        K.wait_flags(st.flags[k, 1:])
+        st.flags[k].zero_()
+        main.wait_event(done)
+        return y
 
 
 SINGLE = Comm(None)

@@ -460,8 +460,10 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
                    K.alloc_act(n, h, prec.act_dtype, dev), bias=P[pfx + "fcs.0.bias"], col_sum=st0[0], col_sumsq=st0[1])
     mean0, rstd0 = _bn_stats(z0, P, pfx + "bns.0.", use_bn, training, comm=comm, pre=st0)
     last_is_input = nl == 0
+    # the pre-scaled SpMM operand is written where the halo exchange wants it (slot 0 of the step's symmetric buffer when pushed)
     x0, cur_s = K.bn_fwd(z0, None, mix if last_is_input else None, mean0, rstd0, P.get(pfx + "bns.0.weight"),
-                         P.get(pfx + "bns.0.bias"), None, use_bn, True, p, seed + 307, gw, dinv, True, not last_is_input)
+                         P.get(pfx + "bns.0.bias"), None, use_bn, True, p, seed + 307, gw, dinv, True, not last_is_input,
+                         ys_out=None if last_is_input else comm.operand_out(n, h, prec.act_dtype, dev))
     if tape is not None:
         tape.update(xin=xin, z0=z0, mean0=mean0, rstd0=rstd0, x0=x0, layers=[], p=p, seed=seed, n=n, training=training,
                     mixed=mix is not None, gw=gw)
@@ -484,7 +486,8 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
         name = f"{pfx}bns.{i + 1}."
         mean, rstd = _bn_stats(z, P, name, use_bn, training, comm=comm, pre=st)
         yo, ys = K.bn_fwd(z, x0 if use_res else None, mix if last else None, mean, rstd, P.get(name + "weight"),
-                          P.get(name + "bias"), None, use_bn, use_act, p, seed + 401 + i, gw, dinv, last, not last)
+                          P.get(name + "bias"), None, use_bn, use_act, p, seed + 401 + i, gw, dinv, last, not last,
+                          ys_out=None if last else comm.operand_out(n, h, prec.act_dtype, dev))
         if tape is not None:
             tape["layers"].append(dict(y=y, z=z, mean=mean, rstd=rstd))
         if last:
@@ -540,7 +543,9 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
             grads[wname] = dw
             grads[f"{pfx}convs.{i}.W.bias"] = colsum
             wt = _w(P, wname, prec, transpose=True)   # [kin, h]
-            dys = K.new_like(dz)
+            dys = comm.operand_out(n, h, prec.act_dtype, dev)
+            if dys is None or dys.stride(0) != dz.stride(0):
+                dys = K.new_like(dz)
             K.gemm_nt([dz_op], [_slice_rows(wt, 0, h)], [(0, 0, 0, 0, h)], h, dys, row_scale=dinv)
             if use_init:
                 if dx0 is None:
@@ -549,7 +554,7 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
                 else:
                     K.gemm_nt([dz_op], [_slice_rows(wt, h, 2 * h)], [(0, 0, 0, 0, h)], h, dx0, accumulate=True)
         else:
-            dys = K.axpby(dz, None, 1.0, 0.0, row_scale=dinv)
+            dys = K.axpby(dz, None, 1.0, 0.0, row_scale=dinv, out=comm.operand_out(n, h, prec.act_dtype, dev))
         # = A^T (dinv . dy): gradient w.r.t. the pre-scaled SpMM input (C4: gradient rows of every shard)
         dy_scaled = comm.spmm_gathered(K.spmm, rowptr_t, col_t, None, dys, heavy=graph.heavy_t)
         dy_plain = None

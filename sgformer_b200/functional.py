@@ -91,6 +91,7 @@ class SGFormerFn(_TapeFunction):
         xin = E.input_operand(x, prec)
         seed = E.next_seed()
         if comm.active:     # row shards hash local row ids: decorrelate the shards' dropout masks
+            comm.begin_step()
             seed = (seed + comm.rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         tt, tg, th = (E.Tape(), E.Tape(), E.Tape()) if need_tape else (None, None, None)
         x1 = E.trans_forward(P, cfg, xin, prec, training, seed, tt, comm=comm)

@@ -33,14 +33,16 @@ class Graph:
     self_loop_mode 0: large/100M GraphConv; 1: PyG gcn_norm (medium GCN).
     `rows=(r0, r1)`: row shard of the global pattern (column ids stay global) for row-sharded multi-GPU runs."""
 
-    def __init__(self, edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None):
+    def __init__(self, edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None,
+                 col_rot: Optional[Tuple[int, int]] = None):
         if not edge_index.is_cuda:
             raise RuntimeError("Graph needs a CUDA edge_index (no CPU fallback)")
         self.n = int(n)
         self.rows = rows
+        self.col_rot = col_rot          # (rot, mod): column ids stored as (col - rot) mod `mod` (row shards with pushed operands)
         self.self_loop_mode = self_loop_mode
         self.edge_index = edge_index
-        self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True, rows=rows)
+        self.rowptr, self.col, self.dinv = K.csr_build(edge_index, self.n, False, self_loop_mode, True, rows=rows, col_rot=col_rot)
         self.heavy = K.heavy_rows(self.rowptr)      # segment plan for hub rows (None on graphs without them)
         self.heavy_t = None
         self._t: Optional[Tuple[Tensor, Tensor]] = None
@@ -52,7 +54,7 @@ class Graph:
     @classmethod
     def _from_parts(cls, n, rowptr, col, dinv, transpose_same: bool):
         g = cls.__new__(cls)
-        g.n, g.rows, g.self_loop_mode, g.edge_index = int(n), None, 0, None
+        g.n, g.rows, g.self_loop_mode, g.edge_index, g.col_rot = int(n), None, 0, None, None
         g.rowptr, g.col, g.dinv = rowptr, col, dinv
         g.heavy = g.heavy_t = None       # batch subgraphs: no per-batch sync for a hub plan
         g._t = (rowptr, col) if transpose_same else None
@@ -82,7 +84,8 @@ class Graph:
                 self._t = (self.rowptr, self.col)      # also true per row shard: rows r0..r1 of A^T == rows of A
                 self.heavy_t = self.heavy
             else:
-                rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)
+                rp, cl, _ = K.csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows,
+                                        col_rot=self.col_rot)
                 self._t = (rp, cl)
                 self.heavy_t = K.heavy_rows(rp)
         return self._t
@@ -92,15 +95,16 @@ _CACHE: "OrderedDict[tuple, Graph]" = OrderedDict()
 _CACHE_MAX = 4
 
 
-def get_graph(edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None) -> Graph:
+def get_graph(edge_index: Tensor, n: int, self_loop_mode: int = 0, rows: Optional[Tuple[int, int]] = None,
+              col_rot: Optional[Tuple[int, int]] = None) -> Graph:
     """Cached Graph for this edge_index tensor (identity: storage pointer, shape, version)."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index, int(n),
-           self_loop_mode, rows)
+           self_loop_mode, rows, col_rot)
     g = _CACHE.get(key)
     if g is not None and g.edge_index is edge_index:
         _CACHE.move_to_end(key)
         return g
-    g = Graph(edge_index, n, self_loop_mode, rows)
+    g = Graph(edge_index, n, self_loop_mode, rows, col_rot)
     _CACHE[key] = g
     while len(_CACHE) > _CACHE_MAX:
         _CACHE.popitem(last=False)

@@ -88,9 +88,10 @@ def new_like(x: Tensor) -> Tensor:
 # graph structure
 # ------------------------------------------------------------------------------------------------
 def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mode: int = 0, want_dinv: bool = True,
-              rows: Optional[Tuple[int, int]] = None):
+              rows: Optional[Tuple[int, int]] = None, col_rot: Optional[Tuple[int, int]] = None):
     """-> (rowptr int64 [n_rows+1], col int32 [nnz'], dinv fp32 [n_rows] | None).  See sgf_csr_build(_rect).
-    `rows=(r0, r1)` builds only that row range of the n x n pattern (row shard; column ids stay global)."""
+    `rows=(r0, r1)` builds only that row range of the n x n pattern (row shard; column ids stay global).
+    `col_rot=(rot, mod)` stores the column ids rotated, (col - rot) mod `mod`, and sorts the rows by them (sgf_csr_build_rot)."""
     _use(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise ValueError("edge_index must be int64 [2, nnz]")
@@ -106,8 +107,9 @@ def csr_build(edge_index: Tensor, n: int, by_source: bool = False, self_loop_mod
     nbytes = C.c_size_t(0)
     check(lib().sgf_csr_build_ws_bytes(nnz, n, C.byref(nbytes)), "sgf_csr_build_ws_bytes")
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    check(lib().sgf_csr_build_rect(_p(ei), nnz, r0, r1, n_cols, int(by_source), self_loop_mode, _p(rowptr), _p(col),
-                                   _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_build_rect")
+    rot, mod = col_rot if col_rot is not None else (0, 0)
+    check(lib().sgf_csr_build_rot(_p(ei), nnz, r0, r1, n_cols, int(by_source), self_loop_mode, rot, mod, _p(rowptr), _p(col),
+                                  _p(dinv), _p(ws), nbytes.value, _stream()), "sgf_csr_build_rot")
     if self_loop_mode == 1 or rows is not None:
         total = int(rowptr[n].item())
         col = col[:total]
@@ -262,6 +264,50 @@ def spmm(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, ou
         e1.record()
         ev.append((e0, e1))
     return out
+
+
+def spmm_flagged(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, flags: Tensor, slot_rows: int,
+                 heavy: Optional[HeavyRows] = None) -> Tensor:
+    """Row-sharded SpMM over the gathered operand x [n_slots*slot_rows, h] whose slots s > 0 are still being pushed by the
+    peers: the kernel consumes slot s once flags[s] != 0 (sgf_spmm_flagged).  col holds rotated ids (csr_build(col_rot=...))."""
+    _use(x)
+    n = rowptr.numel() - 1
+    rows, h, ldx = _mat(x, "x")
+    n_slots = flags.numel()
+    if flags.dtype not in (torch.int32, torch.uint32) or not flags.is_contiguous() or rows != n_slots * slot_rows:
+        raise ValueError("spmm_flagged: flags must be contiguous int32 [n_slots] and x must hold n_slots*slot_rows rows")
+    out = alloc_act(n, h, x.dtype, x.device)
+    _, _, ldy = _mat(out, "out")
+    ev = spmm_events
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rs = _f32vec(row_scale, n, "row_scale")
+    check(lib().sgf_spmm_flagged(_p(rowptr), _p(col), _p(rs), _p(x), ldx, _p(out), ldy, n, h, dcode(x),
+                                 HEAVY_ROW if heavy is not None else 0, _p(flags), slot_rows, n_slots, _stream()), "sgf_spmm_flagged")
+    if heavy is not None:
+        # hub rows touch every slot: wait for all of them, then the segmented path on the complete operand
+        check(lib().sgf_wait_flags(_p(flags[1:]), n_slots - 1, _stream()), "sgf_wait_flags")
+        ns = heavy.seg_start.numel()
+        partial = torch.empty((ns, h), dtype=torch.float32, device=x.device)
+        check(lib().sgf_spmm_heavy(_p(col), _p(rs), _p(x), ldx, _p(out), ldy, h, dcode(x), _p(heavy.seg_start),
+                                   _p(heavy.seg_len), ns, _p(partial), _p(heavy.rows), _p(heavy.seg_ptr), heavy.rows.numel(),
+                                   _stream()), "sgf_spmm_heavy")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
+    return out
+
+
+def wait_flags(flags: Tensor):
+    """Returns (on the current stream) once every entry of the int32 vector `flags` is non-zero."""
+    if flags.numel():
+        check(lib().sgf_wait_flags(_p(flags), flags.numel(), _stream()), "sgf_wait_flags")
+
+
+def signal(flag: Tensor, value: int = 1):
+    """flag[0] = value (release, system scope) on the current stream; `flag` may be a view of a peer GPU's symmetric memory."""
+    check(lib().sgf_signal(_p(flag), value, _stream()), "sgf_signal")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -559,11 +605,12 @@ def bn_finalize(sum_: Optional[Tensor], sumsq: Optional[Tensor], rows: int, h: i
 
 
 def bn_fwd(z: Tensor, res: Optional[Tensor], mix: Optional[Tensor], mean, rstd, gamma, beta, zbias, use_bn: bool,
-           use_relu: bool, p: float, seed: int, gw: float, row_scale: Optional[Tensor], want_y: bool, want_scaled: bool):
+           use_relu: bool, p: float, seed: int, gw: float, row_scale: Optional[Tensor], want_y: bool, want_scaled: bool,
+           ys_out: Optional[Tensor] = None):
     _use(z)
     rows, h, ld = _mat(z, "z")
     y = new_like(z) if want_y else None
-    ys = new_like(z) if want_scaled else None
+    ys = (ys_out if (ys_out is not None and ys_out.stride(0) == ld) else new_like(z)) if want_scaled else None
     _same_ld(ld, res, mix, y, ys)
     check(lib().sgf_bn_fwd(_p(z), _p(res), _p(mix), ld, rows, h, dcode(z), _p(mean), _p(rstd), _p(gamma), _p(beta),
                            _p(zbias), int(use_bn), int(use_relu), p, seed, gw, _p(row_scale), _p(y), _p(ys), _stream()),

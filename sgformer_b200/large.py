@@ -108,7 +108,7 @@ class SGFormer(SGFormerBase):
             # row-sharded: x holds this rank's row block, edge_index is the GLOBAL edge list
             if x.shape[0] != comm.rows[1] - comm.rows[0]:
                 raise ValueError(f"row-sharded forward expects the {comm.rows[1] - comm.rows[0]} rows of this rank, got {x.shape[0]}")
-            graph = get_graph(edge_index, comm.n_global, 0, rows=comm.rows) if self.use_graph else None
+            graph = get_graph(edge_index, comm.n_global, 0, rows=comm.rows, col_rot=comm.col_rot) if self.use_graph else None
         elif isinstance(edge_index, Graph):
             graph = edge_index      # a prebuilt structure (e.g. Graph.subset(idx) of a mini-batch) instead of an edge list
         else:

@@ -16,5 +16,6 @@ def nll_loss_from_logits(logits: torch.Tensor, labels: torch.Tensor, mask: Optio
         raise RuntimeError("sgformer_b200.loss needs CUDA tensors (no CPU fallback)")
     if denom is None:
         denom = float(mask.sum().item()) if mask is not None else float(logits.shape[0])
-    return Fn.SoftmaxNLLFn.apply(logits.float().contiguous() if logits.dtype != torch.float32 or not logits.is_contiguous()
-                                 else logits, labels, mask, denom)
+    # the kernel takes a row pitch: the encoder's padded-pitch logits ([N, 47] inside [N, 48]) are read in place
+    ok = logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    return Fn.SoftmaxNLLFn.apply(logits if ok else logits.float().contiguous(), labels, mask, denom)

@@ -193,7 +193,7 @@ class SGFormer(SGFormerBase):
             gn, gt = _gcn_flat(self.gnn, "gnn.")
             cfg = self._cfg(len(self.gnn.convs), float(self.gnn.dropout), bool(self.gnn.use_bn))
             comm = self._comm
-            graph = get_graph(edge_index, comm.n_global, 1, rows=comm.rows) if comm.active else get_graph(edge_index, x.shape[0], 1)
+            graph = get_graph(edge_index, comm.n_global, 1, rows=comm.rows, col_rot=comm.col_rot) if comm.active else get_graph(edge_index, x.shape[0], 1)
             return Fn.SGFormerFn.apply(x, graph, cfg, prec, self.training, comm, tuple(names) + tuple(gn), *tensors, *gt)
         # foreign GNN module: run it as given, mix + fc on the GPU kernels
         x1 = Fn.TransConvFn.apply(x, self.trans_conv._cfg(), prec, self.training, tn, *tt)

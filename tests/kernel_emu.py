@@ -43,7 +43,7 @@ class Operand:
     planes: int
 
 
-def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True, rows=None):
+def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True, rows=None, col_rot=None):
     src, dst = edge_index[0], edge_index[1]
     if self_loop_mode == 1:
         keep = src != dst
@@ -56,6 +56,9 @@ def csr_build(edge_index, n, by_source=False, self_loop_mode=0, want_dinv=True, 
         nr = rows[1] - rows[0]
     else:
         nr = n
+    if col_rot is not None:      # sgf_csr_build_rot: column ids stored as (col - rot) mod `mod`, rows sorted by them
+        val = (val - col_rot[0]) % col_rot[1]
+        n = max(n, col_rot[1])
     order = torch.argsort(key * n + val, stable=True)
     deg = torch.bincount(key, minlength=nr)
     n = nr
@@ -247,7 +250,7 @@ def _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn):
     return zz, zz
 
 
-def bn_fwd(z, res, mix, mean, rstd, gamma, beta, zbias, use_bn, use_relu, p, seed, gw, row_scale, want_y, want_scaled):
+def bn_fwd(z, res, mix, mean, rstd, gamma, beta, zbias, use_bn, use_relu, p, seed, gw, row_scale, want_y, want_scaled, ys_out=None):
     assert p == 0.0
     _, t = _bn_pre(z, mean, rstd, gamma, beta, zbias, use_bn)
     if use_relu:
@@ -430,11 +433,11 @@ def launch_count():
 
 
 class EmuGraph:
-    def __init__(self, edge_index, n, self_loop_mode=0, rows=None):
-        self.n, self.edge_index, self.self_loop_mode, self.rows = n, edge_index, self_loop_mode, rows
-        self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True, rows=rows)
+    def __init__(self, edge_index, n, self_loop_mode=0, rows=None, col_rot=None):
+        self.n, self.edge_index, self.self_loop_mode, self.rows, self.col_rot = n, edge_index, self_loop_mode, rows, col_rot
+        self.rowptr, self.col, self.dinv = csr_build(edge_index, n, False, self_loop_mode, True, rows=rows, col_rot=col_rot)
         self.heavy = self.heavy_t = None
 
     def transpose(self):
-        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows)
+        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows, col_rot=self.col_rot)
         return rp, cl

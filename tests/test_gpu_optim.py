@@ -34,6 +34,7 @@ def test_adam_matches_torch_two_groups():
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), f"{tuple(a.shape)}: {(a - b).abs().max().item():.3e}"
     st = o1.state_dict()["state"]
     assert set(st[0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(st[0]["step"]) == 7.0
+    assert float(st[3]["step"]) == 6.0          # the parameter that had no gradient once
 
 
 def test_adam_step_count_advances_under_cuda_graph():
@@ -51,13 +52,12 @@ def test_adam_step_count_advances_under_cuda_graph():
     o2.step()
     cg = torch.cuda.CUDAGraph()
     with torch.cuda.graph(cg):
-        o1.step()
-    o2.step()
+        o1.step()                              # captured, not executed
     for _ in range(5):
         cg.replay()
         o2.step()
     torch.cuda.synchronize()
-    assert float(o1.state[p[0]]["step"]) == 8.0
+    assert float(o1.state[p[0]]["step"]) == 7.0
     assert torch.allclose(p[0], q[0], rtol=5e-6, atol=1e-6), (p[0] - q[0]).abs().max().item()
 
 

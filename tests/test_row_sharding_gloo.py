@@ -30,7 +30,7 @@ def _cfg_from_oracle(c):
     return make_config(c["variant"], c["in_channels"], c["hidden"], c["out_channels"], **kw)
 
 
-def _worker(rank, world, port, fixture, outdir):
+def _worker(rank, world, port, fixture, outdir, c4_mode="allgather"):
     for p in (ROOT, HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -50,9 +50,9 @@ def _worker(rank, world, port, fixture, outdir):
     sd = fx["state_dict"]
     names = tuple(sd.keys())
     n = fx["x"].shape[0]
-    comm = Comm(dist.group.WORLD, n)
+    comm = Comm(dist.group.WORLD, n, c4_mode=c4_mode)
     r0, r1 = comm.rows
-    graph = kernel_emu.EmuGraph(fx["edge_index"], n, 1 if cfg["variant"] == "medium" else 0, rows=(r0, r1))
+    graph = kernel_emu.EmuGraph(fx["edge_index"], n, 1 if cfg["variant"] == "medium" else 0, rows=(r0, r1), col_rot=comm.col_rot)
     params = [sd[k].clone().requires_grad_(True) if (sd[k].is_floating_point() and "running" not in k) else sd[k].clone()
               for k in names]
     x = fx["x"][r0:r1].clone().requires_grad_(True)
@@ -71,11 +71,13 @@ def _close(a, b, rtol, atol, what):
     assert err <= atol + rtol * ref, f"{what}: max err {err:.3e} (ref max {ref:.3e})"
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world,c4_mode", [(2, "allgather"), (3, "allgather"), (2, "rotated"), (3, "rotated")])
 @pytest.mark.parametrize("name", ["large_add_init", "large_cat_heads2", "100M_alpha", "medium_gcn"])
-def test_row_sharded_matches_single_process(tmp_path, world, name):
+def test_row_sharded_matches_single_process(tmp_path, world, c4_mode, name):
+    """c4_mode 'rotated' = the slot layout of the pushed halo exchange (rotated column ids in the CSR shard, operand blocks in
+    arrival order) filled by an all-gather; the copy-engine push itself needs GPUs (tests/test_gpu_multi.py)."""
     fixture = os.path.join(GOLD, f"model_{name}.pt")
-    mp.spawn(_worker, args=(world, _free_port(), fixture, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), fixture, str(tmp_path), c4_mode), nprocs=world, join=True)
     fx = torch.load(fixture, weights_only=False)
     parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"), weights_only=False) for r in range(world)]
     out = torch.cat([p["out"] for p in parts])
@@ -99,8 +101,16 @@ def test_partition_and_shard_csr_are_exact():
     g = torch.Generator().manual_seed(0)
     ei = torch.randint(0, n, (2, 900), generator=g)
     full = kernel_emu.csr_build(ei, n)
+    block = blocks[0][1] - blocks[0][0]
     for (r0, r1) in blocks:
         rp, cl, dv = kernel_emu.csr_build(ei, n, rows=(r0, r1))
         assert torch.equal(rp, full[0][r0:r1 + 1] - full[0][r0])
         assert torch.equal(cl, full[1][full[0][r0]:full[0][r1]])
         assert torch.equal(dv, full[2][r0:r1])
+        # rotated storage: same multiset per row, ids shifted so that the shard's own block comes first, rows sorted
+        rpr, clr, dvr = kernel_emu.csr_build(ei, n, rows=(r0, r1), col_rot=(r0, world * block))
+        assert torch.equal(rpr, rp) and torch.equal(dvr, dv)
+        for i in range(r1 - r0):
+            a, b = cl[rp[i]:rp[i + 1]].long(), clr[rp[i]:rp[i + 1]].long()
+            assert torch.equal(torch.sort((a - r0) % (world * block))[0], b)
+            assert bool((b[1:] >= b[:-1]).all())
