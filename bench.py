@@ -326,28 +326,35 @@ def run_full_batch(ctx, wname, w, parallel, steps, warmup, want_e2e=False, want_
 
     for _ in range(warmup):
         step(x, ei, y)
-    # The whole step (zero_grad .. Adam) is a static kernel schedule: capture it once in a CUDA graph and replay it
-    # (single GPU; falls back to eager launches if capture is not possible).
+    # The whole step (zero_grad .. Adam) is a static kernel schedule: capture it once in a CUDA graph and replay it (falls back
+    # to eager launches if capture is not possible).  Multi-GPU steps are captured too - NCCL collectives, the copy-engine pushes
+    # of the halo exchange and their flag kernels are all graph nodes - and every rank replays only if every rank captured.
     run_step = lambda: step(x, ei, y)  # noqa: E731
     used_graph = False
-    if world == 1 and use_graph:
+    if use_graph and (world == 1 or os.environ.get("SGF_BENCH_MULTI_GRAPH", "1") == "1"):
+        cg = None
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 step(x, ei, y)
             torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):
                 step(x, ei, y)
+        except Exception as exc:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            cg = None
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if cg is not None else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
             cg.replay()
             torch.cuda.synchronize()
             run_step = cg.replay
             used_graph = True
-        except Exception as exc:  # pragma: no cover
-            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
-            run_step = lambda: step(x, ei, y)  # noqa: E731
     graph = get_graph(ei, n, 0, rows=comm.rows, col_rot=comm.col_rot) if rows_mode else get_graph(ei, n, 0)
     nnz = graph.nnz
     sampler = ClockSampler(ctx.local) if (rank == 0 and sample_clocks) else None

@@ -1103,8 +1103,9 @@ extern "C" int sgf_ln_bwd_attn(const void* dy, const void* o, const void* r, con
     if (use_ln && (!gamma || !beta || !stats)) return SGF_ERR_ARG;
     if (rows == 0) return SGF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // resident CTAs per SM for the one-chunk-per-lane geometry: 3 (80 registers, ~20 spilled to L1) or 2 (no spills); A/B on the GPU
-    static const int minb = [] { const char* e = getenv("SGF_LNATTN_BLOCKS"); return (e && e[0] == '2') ? 2 : 3; }();
+    // resident CTAs per SM for the one-chunk-per-lane geometry: 2 (118 registers, no spills; default) or 3 (80 registers, ~20
+    // spilled): measured on a B200 at the products shape 89.58 vs 89.75 ms/step (r2b), i.e. no difference
+    static const int minb = [] { const char* e = getenv("SGF_LNATTN_BLOCKS"); return (e && e[0] == '3') ? 3 : 2; }();
     if (minb == 2 && !use_relu) {
         SGF_DISPATCH_T_CPL_DROP(dtype, g.cpl, p > 0.f, (ln_bwd_attn_kernel<T, CPL, DROP, false, 2><<<row_grid(rows, g), kRowBlock, h * sizeof(float), st>>>(
                                              (const T*)dy, (const T*)o, (const T*)r, (const T*)xa, ld, rows, h, g.chunks, g.lpr_log2, a, b,

@@ -322,6 +322,45 @@ def trans_forward(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precisi
     return x
 
 
+def trans_attentions(P: Dict[str, Tensor], cfg: dict, xin: K.Operand, prec: Precision, with_act: bool,
+                     pfx: str = "trans_conv.") -> List[Tensor]:
+    """TransConv.get_attentions (large/ours.py:221-238, medium/ours.py:162-177, 100M/ours.py:274-289): per attention layer the
+    [N, N] visualisation matrix  mean_h(q~_h k~_h^T) / mean_h(q~_h . sum_l k~_l + N)  of large/ours.py:152-155.  The N x N product is one
+    tensor-core GEMM of the concatenated heads (sum over heads of per-head dot products) with 1/(H ||q|| ||k||) read from the
+    device and the row normaliser as its row scale; the layer stack itself runs the un-fused attention (q, k materialised).
+    Inference only (no dropout, no tape), O(N^2) memory like the reference: meant for small graphs."""
+    h, H, d_in = cfg["hidden"], cfg["num_heads"], cfg["in_channels"]
+    check_width(h, prec, "hidden_channels")
+    n = xin.rows
+    dev = xin.data.device
+    use_ln = bool(cfg["trans_use_bn"])
+    ca, cb, use_res = _res_coef(cfg)
+    use_weight = bool(cfg["trans_use_weight"])
+    t0 = K.gemm_nt([xin], [_w(P, pfx + "fcs.0.weight", prec)], [(0, 0, 0, 0, d_in)], h, K.alloc_act(n, h, prec.act_dtype, dev),
+                   bias=P[pfx + "fcs.0.bias"])
+    x, _ = K.ln_fwd(t0, None, 1.0, 0.0, P.get(pfx + "bns.0.weight"), P.get(pfx + "bns.0.bias"), use_ln, True, 0.0, 0, False)
+    out = []
+    for i in range(cfg["trans_num_layers"]):
+        lp = f"{pfx}convs.{i}."
+        wcat, bcat = _qkv_weight(P, lp, use_weight)
+        nout = wcat.shape[0]
+        qkv = torch.empty((n, K.ceil_to(nout, 8)), dtype=prec.act_dtype, device=dev)[:, :nout]
+        K.gemm_nt([K.as_operand(x, prec.planes)], [K.pack_operand(wcat, False, prec.planes)], [(0, 0, 0, 0, h)], nout, qkv, bias=bcat)
+        q, k = qkv[:, :H * h], qkv[:, H * h:2 * H * h]
+        v = qkv[:, 2 * H * h:] if use_weight else x
+        at = Tape()
+        o = attention_forward(q, k, v, H, prec, at)
+        inv_norm = at["den"].mean(dim=0).reciprocal_().contiguous()       # [N]: 1 / mean_h(den_h)  (an [N]-vector; not a hot path)
+        att = K.alloc_act(n, n, torch.float32, dev)
+        K.gemm_nt([K.as_operand(q, prec.planes)], [K.as_operand(k, prec.planes)], [(0, 0, 0, 0, H * h)], n, att, alpha=1.0 / H,
+                  alpha_dev=at["scal"][2:3], row_scale=inv_norm)
+        out.append(att)
+        a = K.head_mean(o, H, h) if H > 1 else o
+        x, _ = K.ln_fwd(a, x if use_res else None, ca, cb, P.get(f"{pfx}bns.{i + 1}.weight"), P.get(f"{pfx}bns.{i + 1}.bias"), use_ln,
+                        with_act and bool(cfg["trans_use_act"]), 0.0, 0, False)
+    return out
+
+
 def trans_backward(P, cfg: dict, tape: Tape, dout: Tensor, gscale: float, prec: Precision, grads: Dict[str, Tensor],
                    pfx: str = "trans_conv.", want_dx: bool = False, comm: Comm = SINGLE) -> Optional[Tensor]:
     h, H, d_in = cfg["hidden"], cfg["num_heads"], cfg["in_channels"]

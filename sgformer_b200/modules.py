@@ -159,27 +159,18 @@ class TransConvBase(_Base):
         return Fn.TransConvFn.apply(x, self._cfg(), E.precision(self.precision), self.training, names, *tensors)
 
     def _attentions(self, x: Tensor, with_act: bool) -> Tensor:
-        """get_attentions (large/ours.py:221-238; medium/100M skip the activation)."""
-        layer_, attentions = [], []
-        x = F.linear(x, self.fcs[0].weight, self.fcs[0].bias)
-        if self.use_bn:
-            x = self.bns[0](x)
-        x = F.relu(x)
-        layer_.append(x)
-        for i, conv in enumerate(self.convs):
-            x, attn = conv._attend(x, x, output_attn=True)
-            attentions.append(attn)
-            if self._use_residual():
-                if self.variant == "large":
-                    x = (x + layer_[i]) / 2.0
-                else:
-                    x = self.alpha * x + (1 - self.alpha) * layer_[i]
-            if self.use_bn:
-                x = self.bns[i + 1](x)
-            if with_act and self.use_act:
-                x = F.relu(x)
-            layer_.append(x)
-        return torch.stack(attentions, dim=0)
+        """get_attentions (large/ours.py:221-238; medium/100M skip the activation) -> [layers, N, N], on the kernels
+        (engine.trans_attentions).  CPU inputs are computed on cuda:0 and copied back, like forward."""
+        _require_cuda("get_attentions")
+        names, tensors = self._flat("trans_conv.")
+        host = not x.is_cuda
+        dev = torch.device("cuda", torch.cuda.current_device()) if host else x.device
+        with torch.no_grad():
+            P = {n_: (t.to(dev) if host else t) for n_, t in zip(names, tensors)}
+            prec = E.precision(self.precision)
+            atts = E.trans_attentions(P, self._cfg(), E.input_operand(x.to(dev), prec), prec, with_act)
+            out = torch.stack([a.contiguous() for a in atts], dim=0)
+        return out.to(x.device) if host else out
 
 
 # =================================================================================================

@@ -230,7 +230,26 @@ def graph_prep_cases():
     print("graph_prep", {k: tuple(v["prepared"].shape) for k, v in out.items()})
 
 
+def get_attentions_cases():
+    """TransConv.get_attentions of the unmodified reference (large/ours.py:221-238 and the medium / 100M variants): the [layers, N, N]
+    visualisation matrices, for the model fixtures whose graphs are small enough (N <= 257)."""
+    out = {}
+    for name in ("large_add_init", "large_cat_heads2", "large_noweight", "100M_alpha", "medium_res_heads2"):
+        fx = torch.load(os.path.join(GOLD, f"model_{name}.pt"), weights_only=False)
+        model, _ = build_reference_model(fx["cfg"]["variant"], fx["cfg"])
+        model.load_state_dict(fx["state_dict"])
+        model.eval()
+        with torch.no_grad():
+            att = model.get_attentions(fx["x"])
+        out[name] = att.clone()
+        print("get_attentions", name, tuple(att.shape), float(att.abs().max()))
+    torch.save(out, os.path.join(GOLD, "get_attentions.pt"))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "get_attentions":      # add this fixture without regenerating the others
+        get_attentions_cases()
+        sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     for nm, sp in CASES.items():
         model_case(nm, sp)
@@ -238,3 +257,4 @@ if __name__ == "__main__":
     graphconv_layer_cases()
     evaluate_cases()
     graph_prep_cases()
+    get_attentions_cases()

@@ -140,6 +140,24 @@ def test_full_attention_conv_golden(precision, tol):
     assert att.shape == (q.shape[0], q.shape[0])
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_get_attentions_golden(precision, tol):
+    """SGFormer.get_attentions on the kernels (engine.trans_attentions) == the reference's [layers, N, N] matrices
+    (large/ours.py:221-238, medium/ours.py:162-177, 100M/ours.py:274-289), CUDA and CPU inputs."""
+    fx = torch.load(os.path.join(GOLD, "get_attentions.pt"), weights_only=False)
+    for name, ref in fx.items():
+        m = torch.load(os.path.join(GOLD, f"model_{name}.pt"), weights_only=False)
+        model = build_model(m["cfg"]).to(DEV).set_precision(precision)
+        model.load_state_dict(m["state_dict"])
+        model.eval()
+        att = model.get_attentions(m["x"].to(DEV))
+        assert att.shape == ref.shape and att.is_cuda
+        _close(att, ref, tol, 0, f"{name} get_attentions")
+    att_cpu = model.get_attentions(m["x"])          # host tensors: computed on the device, returned on the host
+    assert not att_cpu.is_cuda
+    _close(att_cpu, ref, tol, 0, "get_attentions (cpu input)")
+
+
 def test_graphconv_layer_golden():
     from sgformer_b200.large import GraphConvLayer
     fx = torch.load(os.path.join(GOLD, "graphconv_layer.pt"), weights_only=False)

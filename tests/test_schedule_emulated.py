@@ -75,6 +75,19 @@ def test_attention_fn_matches_reference():
             _close(g, c[t], 1e-3, 1e-7, f"{name} {t}")
 
 
+def test_get_attentions_matches_reference():
+    """engine.trans_attentions (kernel path of TransConv.get_attentions) against the reference's own get_attentions output."""
+    fx = torch.load(os.path.join(GOLD, "get_attentions.pt"), weights_only=False)
+    for name, ref in fx.items():
+        m = torch.load(os.path.join(GOLD, f"model_{name}.pt"), weights_only=False)
+        cfg = _cfg_from_oracle(m["cfg"])
+        P = {k: v for k, v in m["state_dict"].items() if k.startswith("trans_conv.")}
+        atts = E.trans_attentions(P, cfg, kernel_emu.pack_operand(m["x"], False, 3), E.FP32, with_act=cfg["variant"] == "large")
+        got = torch.stack(atts, 0)
+        assert got.shape == ref.shape
+        _close(got, ref, 1e-4, 1e-9, f"get_attentions {name}")
+
+
 def test_bf16_schedule_is_close():
     fx = torch.load(os.path.join(GOLD, "model_large_add_init.pt"), weights_only=False)
     cfg = _cfg_from_oracle(fx["cfg"])
