@@ -64,8 +64,14 @@ class _PushState:
         hdl = symm.rendezvous(self.flags, self.group)
         self.peer_flags = [hdl.get_buffer(r, (MAX_PUSH_BUFFERS, w), torch.int32) for r in range(w)]
         self.side = torch.cuda.Stream(device=device, priority=-1)
+        # First peer copy NOW, while every GPU is quiescent: torch enables peer access (and creates its context on the peer device)
+        # lazily inside the first cross-device copy_, a host call that waits for the peer device to go idle - which it never does once
+        # that device runs a flagged SpMM spinning on this very rank's push (observed: both ranks trap after the spin limit).
+        for r in range(w):
+            if r != comm.rank:
+                self.peer_flags[r][MAX_PUSH_BUFFERS - 1, comm.rank:comm.rank + 1].copy_(self.flags[0, 0:1])
         torch.cuda.synchronize(device)
-        dist.barrier(group=self.group)       # every rank's flags are zero before anybody signals
+        dist.barrier(group=self.group)       # every rank's flags are zero (the warm-up wrote zeros) before anybody signals
 
     def buffer(self, k: int):
         if k not in self.bufs:
