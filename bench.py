@@ -227,7 +227,8 @@ class Ctx:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
             self.dist = dist
 
     def barrier(self):
@@ -567,6 +568,32 @@ def extras(ctx, args):
     return out
 
 
+def extras_in_children(ctx, args):
+    """N > 1: the extra measurements run in a second set of processes (one child per rank, its own rendezvous port and NCCL
+    communicator, the same GPU) so that whatever happens to them - a failed collective, a trapped kernel - cannot take the headline
+    line down; the parents idle meanwhile with their caches released."""
+    gc.collect()
+    torch.cuda.empty_cache()
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 23)
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--extras-child", "--gpus", str(args.gpus), "--steps", str(args.steps),
+           "--warmup", str(args.warmup)]
+    out = None
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("EXTRAS_JSON "):
+                out = json.loads(ln[len("EXTRAS_JSON "):])
+        if out is None and ctx.rank == 0:
+            out = {"error": f"extras child exited with {r.returncode}: " + (r.stderr.strip().splitlines() or [""])[-1][:300]}
+    except Exception as exc:
+        if ctx.rank == 0:
+            out = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    ctx.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -579,6 +606,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (the other BASELINE configurations)")
+    ap.add_argument("--extras-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--rmat", action="store_true", help="power-law R-MAT edges instead of uniform (secondary, not graded)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     ap.add_argument("--parallel", default="dp", choices=["dp", "rows"],
@@ -595,6 +623,13 @@ def main():
     ctx = Ctx()
     rank, world = ctx.rank, ctx.world
     n, d, c, h = w["n"], w["d"], w["c"], w["h"]
+    if args.extras_child:
+        out = extras(ctx, args)
+        if rank == 0:
+            print("EXTRAS_JSON " + json.dumps(out), flush=True)
+        if world > 1:
+            ctx.dist.destroy_process_group()
+        return
 
     if "batch" in w:
         r = run_minibatch(ctx, w, args.steps, args.warmup)
@@ -621,7 +656,7 @@ def main():
     ctx.barrier()
     extra = None
     if not args.no_extra and args.workload == "products" and not args.rmat:
-        extra = extras(ctx, args)
+        extra = extras(ctx, args) if world == 1 else extras_in_children(ctx, args)
     if rank != 0:
         if world > 1:
             ctx.dist.destroy_process_group()

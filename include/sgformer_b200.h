@@ -138,6 +138,10 @@ int sgf_spmm_flagged(const int64_t* rowptr, const int32_t* col, const float* row
                      int n_slots, void* stream);
 /* *flag = value with release semantics at system scope (flag may live in a peer GPU's memory): "my block has landed". */
 int sgf_signal(uint32_t* flag, uint32_t value, void* stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: the copy-engine transfer of an operand block into a peer GPU's
+ * symmetric buffer (dst = the peer mapping of that buffer).  A plain stream-ordered memcpy node: no cross-device stream
+ * synchronisation and capturable in a CUDA graph (torch's cross-device Tensor.copy_ is neither). */
+int sgf_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
 /* returns (on the stream) once flags[0..n) are all non-zero */
 int sgf_wait_flags(const uint32_t* flags, int n, void* stream);
 

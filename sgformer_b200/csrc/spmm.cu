@@ -443,6 +443,13 @@ extern "C" int sgf_signal(uint32_t* flag, uint32_t value, void* stream) {
     return SGF_OK;
 }
 
+extern "C" int sgf_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return SGF_ERR_ARG;
+    if (bytes == 0) return SGF_OK;
+    SGF_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return SGF_OK;
+}
+
 extern "C" int sgf_wait_flags(const uint32_t* flags, int n, void* stream) {
     if (!flags || n < 0) return SGF_ERR_ARG;
     if (n == 0) return SGF_OK;

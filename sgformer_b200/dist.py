@@ -15,7 +15,9 @@ referenced by some local row, so the halo of a rank IS the other ranks' blocks; 
 
   push       fused compute + exchange.  Every rank owns a symmetric buffer [world*block, h] per SpMM of the step.  The producer of the
              operand writes its block straight into slot 0; the rank then PUSHES the block into slot (rank - r) mod world of every peer
-             r with copy-engine peer copies over NVLink (a side stream: no SMs, no NCCL kernels) and raises the peer's arrival flag.
+             r with copy-engine peer copies over NVLink (a side stream: no SMs, no NCCL kernels) and raises the peer's arrival flag
+             with a second, 4-byte copy-engine write behind it (a flag KERNEL cannot be used: it is not scheduled while the
+             consumer's SpMM occupies the SMs spinning on that very flag).
              The SpMM (`sgf_spmm_flagged`) starts immediately on the local slot: the CSR shard stores ROTATED column ids
              (`sgf_csr_build_rot`), so every row meets its neighbours in arrival order and a warp waits only when it reaches a slot
              whose flag is still down.  The consumer lowers its flags after the SpMM; the step's collectives (C1 / C5) order the reuse
@@ -64,12 +66,14 @@ class _PushState:
         hdl = symm.rendezvous(self.flags, self.group)
         self.peer_flags = [hdl.get_buffer(r, (MAX_PUSH_BUFFERS, w), torch.int32) for r in range(w)]
         self.side = torch.cuda.Stream(device=device, priority=-1)
-        # First peer copy NOW, while every GPU is quiescent: torch enables peer access (and creates its context on the peer device)
-        # lazily inside the first cross-device copy_, a host call that waits for the peer device to go idle - which it never does once
-        # that device runs a flagged SpMM spinning on this very rank's push (observed: both ranks trap after the spin limit).
+        # First peer copy NOW, while every GPU is quiescent (any lazy driver-side set-up of the peer mapping happens here, not while a
+        # flagged SpMM spins on this very rank's push).
+        from . import kernels as K
+        K._use(self.flags)
+        self.one = torch.ones(1, dtype=torch.int32, device=device)     # source of the arrival flags (copied by the copy engine)
         for r in range(w):
             if r != comm.rank:
-                self.peer_flags[r][MAX_PUSH_BUFFERS - 1, comm.rank:comm.rank + 1].copy_(self.flags[0, 0:1])
+                K.memcpy_async(self.peer_flags[r][MAX_PUSH_BUFFERS - 1, comm.rank:comm.rank + 1], self.flags[0, 0:1])
         torch.cuda.synchronize(device)
         dist.barrier(group=self.group)       # every rank's flags are zero (the warm-up wrote zeros) before anybody signals
 
@@ -245,8 +249,11 @@ class Comm:
             st.side.wait_event(ready)
             for s in range(1, w):                    # my block is slot s of rank (rank - s): nearest consumer position first
                 r = (rank - s) % w
-                peers[r][s * b:s * b + n_loc].copy_(own, non_blocking=True)      # copy-engine peer copy over NVLink
-                K.signal(st.peer_flags[r][k, s:s + 1], 1)
+                K.memcpy_async(peers[r][s * b:s * b + n_loc], own)               # copy-engine peer copy over NVLink
+                # ... and the arrival flag behind it, ALSO by the copy engine: a 1-thread flag kernel of another stream is never
+                # scheduled while the consumer's flagged SpMM holds the SMs spinning (measured on B200: tests/push_debug2.py stages
+                # S1/P2 trap, S2/P1 pass), whereas stream-ordered copy-engine writes need no SM
+                K.memcpy_async(st.peer_flags[r][k, s:s + 1], st.one)
             done = torch.cuda.Event()
             done.record(st.side)
         y = K.spmm_flagged(rowptr, col, row_scale, buf, st.flags[k], b, heavy=heavy)

@@ -299,6 +299,15 @@ def spmm_flagged(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Te
     return out
 
 
+def memcpy_async(dst: Tensor, src: Tensor):
+    """Stream-ordered raw copy src -> dst (same byte size, both contiguous) on the current stream; dst may be the mapping of a
+    peer GPU's symmetric buffer (sgf_memcpy_async: copy engine over NVLink, no cross-device stream synchronisation)."""
+    nb = src.numel() * src.element_size()
+    if not (dst.is_contiguous() and src.is_contiguous()) or dst.numel() * dst.element_size() != nb:
+        raise ValueError("memcpy_async: contiguous tensors of equal byte size expected")
+    check(lib().sgf_memcpy_async(_p(dst), _p(src), nb, _stream()), "sgf_memcpy_async")
+
+
 def wait_flags(flags: Tensor):
     """Returns (on the current stream) once every entry of the int32 vector `flags` is non-zero."""
     if flags.numel():
