@@ -136,6 +136,18 @@ int sgf_spmm_heavy(const int32_t* col, const float* row_scale, const void* x, in
 int sgf_spmm_flagged(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y,
                      int64_t ldy, int64_t n_rows, int h, int dtype, int64_t max_row_len, const uint32_t* flags, int64_t slot_rows,
                      int n_slots, void* stream);
+/* One PHASE of a row-sharded SpMM (dist.Comm, C4 overlap): entries [lo[r], hi[r]) of every row r (int32 offsets relative to the row
+ * start, from sgf_csr_row_splits; NULL = row start / row end) are gathered and added to part_in[r,:] (fp32, nullable); the result
+ * goes to part_out[r,:] (fp32 partial sums, pitch ld_part) or, when part_out is NULL, is scaled by row_scale[r] and stored to
+ * y[r,:] like sgf_spmm.  With the rotated column ids of sgf_csr_build_rot a range is "the neighbours living in slots a..b of the
+ * gathered operand": the phase of the local slot runs while the peers' blocks are still in flight, each later phase is launched
+ * behind an sgf_wait_flags on the slots it needs. */
+int sgf_spmm_range(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y,
+                   int64_t ldy, int64_t n_rows, int h, int dtype, const int32_t* lo, const int32_t* hi, const float* part_in,
+                   float* part_out, int64_t ld_part, void* stream);
+/* splits[t*n_rows + r] = number of entries of row r with column id < thresholds[t] (rows sorted; device int32 thresholds) */
+int sgf_csr_row_splits(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* thresholds, int n_thr,
+                       int32_t* splits, void* stream);
 /* *flag = value with release semantics at system scope (flag may live in a peer GPU's memory): "my block has landed". */
 int sgf_signal(uint32_t* flag, uint32_t value, void* stream);
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`: the copy-engine transfer of an operand block into a peer GPU's

@@ -152,6 +152,25 @@ __global__ void csr_rotate_cols_kernel(int32_t* __restrict__ col, const int64_t*
     }
 }
 
+// splits[t][r] = number of entries of row r whose (sorted) column id is < thr[t]  (binary search; thresholds ascending)
+__global__ void csr_row_splits_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, int n_thr,
+                                      const int32_t* __restrict__ thr, int32_t* __restrict__ splits) {
+    const int64_t total = n * n_thr;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int t = (int)(i / n);
+        const int64_t r = i - (int64_t)t * n;
+        const int64_t s = rowptr[r];
+        int64_t lo = s, hi = rowptr[r + 1];
+        const int32_t key = thr[t];
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (col[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        splits[i] = (int32_t)(lo - s);
+    }
+}
+
 __global__ void csr_add_loops_kernel(int64_t n, int64_t row_begin, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
                                      int32_t* __restrict__ col) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -594,6 +613,15 @@ extern "C" int sgf_csr_build_rot(const int64_t* edge_index, int64_t nnz, int64_t
     } else {
         SGF_CUDA_TRY(cudaMemsetAsync(rowptr, 0, 8, st));
     }
+    return SGF_OK;
+}
+
+extern "C" int sgf_csr_row_splits(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const int32_t* thresholds, int n_thr,
+                                  int32_t* splits, void* stream) {
+    if (!rowptr || n_rows < 0 || n_thr < 0 || (n_thr > 0 && (!thresholds || !splits))) return SGF_ERR_ARG;
+    if (n_rows == 0 || n_thr == 0) return SGF_OK;
+    csr_row_splits_kernel<<<grid_for(n_rows * n_thr, 256), 256, 0, (cudaStream_t)stream>>>(rowptr, col, n_rows, n_thr, thresholds, splits);
+    SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }
 

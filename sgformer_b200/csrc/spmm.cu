@@ -137,6 +137,81 @@ __device__ __forceinline__ void gather_range_flagged(const int32_t* __restrict__
 // below.  SGF_SPMM_PIPELINE=1 software-pipelines the dependent chain rowptr -> column ids -> feature rows across the warp's work
 // items (an item = up to 32 neighbours of one row): while the gathers of item i are in flight, the column ids of item i+1 (same
 // row or the warp's next row) and the rowptr entries of the row after next are already loading (slower on B200, see above).
+// Row range of a phased SpMM (row-sharded runs, dist.Comm._spmm_phased): the launch handles entries [lo[r], hi[r]) of every row r
+// (offsets relative to the row start; null = row start / row end), starts from the fp32 partial sums of the previous phases
+// (part_in, nullable) and either hands fp32 partials on (part_out) or scales and stores the finished row.
+struct RowRange {
+    const int32_t* lo;
+    const int32_t* hi;
+    const float* part_in;
+    float* part_out;
+    int64_t ld_part;
+};
+template <typename T, int CPL>
+__global__ void __launch_bounds__(kSpmmBlock, kMinBlocks)
+spmm_range_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
+                  const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy, int64_t n_rows, int chunks, int lpr_log2,
+                  RowRange rr) {
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int lpr = 1 << lpr_log2;
+    const int groups = 32 >> lpr_log2;
+    const int grp = lane >> lpr_log2;
+    const int sub = lane & (lpr - 1);
+    const int64_t warp0 = ((int64_t)blockIdx.x * kSpmmBlock + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kSpmmBlock) >> 5;
+    int coff[CPL];
+    bool cval[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        int ch = sub + c * lpr;
+        cval[c] = ch < chunks;
+        coff[c] = ch * VN;
+    }
+    for (int64_t r = warp0; r < n_rows; r += nwarps) {
+        const int64_t s0 = rowptr[r];
+        const int64_t s = rr.lo ? s0 + rr.lo[r] : s0;
+        const int64_t e = rr.hi ? s0 + rr.hi[r] : rowptr[r + 1];
+        float acc[CPL][VN];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[c][i] = 0.f;
+        gather_range<T, CPL>(col, x, ldx, s, e, lane, groups, grp, coff, cval, acc);
+        for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+#pragma unroll
+                for (int i = 0; i < VN; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], o);
+        }
+        if (grp == 0) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (!cval[c]) continue;
+                if (rr.part_in) {
+                    const float4* pi = reinterpret_cast<const float4*>(rr.part_in + r * rr.ld_part + coff[c]);
+#pragma unroll
+                    for (int q = 0; q < VN / 4; ++q) {
+                        const float4 v = pi[q];
+                        acc[c][4 * q] += v.x; acc[c][4 * q + 1] += v.y; acc[c][4 * q + 2] += v.z; acc[c][4 * q + 3] += v.w;
+                    }
+                }
+                if (rr.part_out) {
+                    float4* po = reinterpret_cast<float4*>(rr.part_out + r * rr.ld_part + coff[c]);
+#pragma unroll
+                    for (int q = 0; q < VN / 4; ++q) po[q] = make_float4(acc[c][4 * q], acc[c][4 * q + 1], acc[c][4 * q + 2], acc[c][4 * q + 3]);
+                } else {
+                    const float rs = row_scale ? row_scale[r] : 1.0f;
+                    float f[VN];
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) f[i] = acc[c][i] * rs;
+                    stg_na(y + r * ldy + coff[c], Vec16<T>::pack(f));
+                }
+            }
+        }
+    }
+}
+
 template <typename T, int CPL, bool FLAGS = false>
 __global__ void __launch_bounds__(kSpmmBlock, kMinBlocks)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ row_scale,
@@ -374,6 +449,43 @@ static int launch_spmm(const int64_t* rowptr, const int32_t* col, const float* r
 }
 
 template <typename T>
+static int launch_range(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y,
+                        int64_t ldy, int64_t n_rows, int h, const RowRange& rr, cudaStream_t st) {
+    constexpr int VN = Vec16<T>::N;
+    if (h % VN != 0 || ldx % VN != 0 || (y && ldy % VN != 0) || rr.ld_part % 4 != 0) return SGF_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(rr.part_in) & 15) ||
+        (reinterpret_cast<uintptr_t>(rr.part_out) & 15))
+        return SGF_ERR_ARG;
+    const int chunks = h / VN;
+    int lpr_log2 = 0;
+    while ((1 << lpr_log2) < chunks && lpr_log2 < 5) ++lpr_log2;
+    const int lpr = 1 << lpr_log2;
+    const int cpl = (chunks + lpr - 1) / lpr;
+    if (n_rows == 0) return SGF_OK;
+    int64_t blocks = (n_rows * 32 + kSpmmBlock - 1) / kSpmmBlock;
+    int64_t cap = (int64_t)num_sms() * kMinBlocks * 8;
+    if (blocks > cap) blocks = cap;
+    const T* xp = static_cast<const T*>(x);
+    T* yp = static_cast<T*>(y);
+#define SGF_RANGE_CASE(N)                                                                                             \
+    case N:                                                                                                           \
+        spmm_range_kernel<T, N><<<(unsigned)blocks, kSpmmBlock, 0, st>>>(rowptr, col, row_scale, xp, ldx, yp, ldy,     \
+                                                                         n_rows, chunks, lpr_log2, rr);                \
+        break;
+    switch (cpl) {
+        SGF_RANGE_CASE(1)
+        SGF_RANGE_CASE(2)
+        SGF_RANGE_CASE(3)
+        SGF_RANGE_CASE(4)
+        default: return SGF_ERR_UNSUPPORTED;
+    }
+#undef SGF_RANGE_CASE
+    SGF_LAUNCH_CHECK();
+    count_launch();
+    return SGF_OK;
+}
+
+template <typename T>
 static int launch_heavy(const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y, int64_t ldy, int h,
                         const int64_t* seg_start, const int32_t* seg_len, int64_t n_seg, float* partial,
                         const int64_t* heavy_rows, const int64_t* heavy_seg_ptr, int64_t n_heavy, cudaStream_t st) {
@@ -433,6 +545,18 @@ extern "C" int sgf_spmm_flagged(const int64_t* rowptr, const int32_t* col, const
     const sgf::SlotWait sw{flags, slot_rows, n_slots};
     if (dtype == 0) return sgf::launch_spmm<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st, &sw);
     if (dtype == 1) return sgf::launch_spmm<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, max_row_len, st, &sw);
+    return SGF_ERR_ARG;
+}
+
+extern "C" int sgf_spmm_range(const int64_t* rowptr, const int32_t* col, const float* row_scale, const void* x, int64_t ldx, void* y,
+                              int64_t ldy, int64_t n_rows, int h, int dtype, const int32_t* lo, const int32_t* hi,
+                              const float* part_in, float* part_out, int64_t ld_part, void* stream) {
+    if (!rowptr || n_rows < 0 || h <= 0 || (n_rows > 0 && !x) || (!part_out && n_rows > 0 && !y)) return SGF_ERR_ARG;
+    if ((part_in || part_out) && ld_part < h) return SGF_ERR_ARG;
+    const sgf::RowRange rr{lo, hi, part_in, part_out, ld_part};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0) return sgf::launch_range<float>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, rr, st);
+    if (dtype == 1) return sgf::launch_range<__nv_bfloat16>(rowptr, col, row_scale, x, ldx, y, ldy, n_rows, h, rr, st);
     return SGF_ERR_ARG;
 }
 

@@ -18,10 +18,13 @@ referenced by some local row, so the halo of a rank IS the other ranks' blocks; 
              r with copy-engine peer copies over NVLink (a side stream: no SMs, no NCCL kernels) and raises the peer's arrival flag
              with a second, 4-byte copy-engine write behind it (a flag KERNEL cannot be used: it is not scheduled while the
              consumer's SpMM occupies the SMs spinning on that very flag).
-             The SpMM (`sgf_spmm_flagged`) starts immediately on the local slot: the CSR shard stores ROTATED column ids
-             (`sgf_csr_build_rot`), so every row meets its neighbours in arrival order and a warp waits only when it reaches a slot
-             whose flag is still down.  The consumer lowers its flags after the SpMM; the step's collectives (C1 / C5) order the reuse
-             of a buffer between steps.
+             The CSR shard stores ROTATED column ids (`sgf_csr_build_rot`): a row's neighbours are sorted by arrival slot.  The SpMM
+             runs in PHASES over groups of slots (`sgf_spmm_range` + per-row split offsets): the phase of the local slot starts at
+             once and hides the transfer, every later phase is launched behind a tiny `sgf_wait_flags` on the slots it reads and
+             carries the rows' fp32 partial sums forward.  (A single kernel that waits inside each row, `sgf_spmm_flagged`,
+             is correct but overlaps nothing: every warp stalls in its FIRST row until the last slot has landed - measured
+             5.7 ms vs 4.9 ms of pure gather at 2 GPUs; kept as SGF_C4_MODE=push-flagged.)  The consumer lowers its flags after the
+             SpMM; the step's collectives (C1 / C5) order the reuse of a buffer between steps.
   rotated    the same rotated layout filled by one all-gather (CPU tests of the layout; no overlap).
   allgather  r1 behaviour: blocking all-gather of the blocks in rank order, plain SpMM.
 """
@@ -106,9 +109,19 @@ class Comm:
             mode = "push" if (self.active and self.world > 1 and dist.get_backend(group) == "nccl") else "allgather"
         if not self.active or self.world == 1:
             mode = "allgather"
-        if mode not in ("push", "rotated", "allgather"):
+        if mode not in ("push", "push-flagged", "rotated", "allgather"):
             raise ValueError(f"unknown C4 mode {mode!r}")
         self.c4_mode = mode
+        # slot groups of the phased SpMM: every slot its own phase up to 4 GPUs, else the local slot + 3 groups of remote slots
+        # (each phase boundary costs one fp32 write + read of the partial sums, each group delays its slots to the last arrival)
+        ng = int(os.environ.get("SGF_C4_GROUPS", "0")) or min(self.world, 4)
+        ng = max(1, min(ng, self.world))
+        if ng == 1:
+            self.groups = [(0, self.world)]
+        else:
+            rest, k = self.world - 1, ng - 1
+            cuts = [1 + (rest * i) // k for i in range(k + 1)]
+            self.groups = [(0, 1)] + [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
         self._push = {}            # (h, dtype) -> _PushState
         self._spmm_calls = 0       # position of the next SpMM inside the current step (selects the symmetric buffer)
         self._push_failed = False
@@ -116,7 +129,7 @@ class Comm:
     # column-id rotation the CSR shard of this rank must be built with (None: global ids)
     @property
     def col_rot(self) -> Optional[Tuple[int, int]]:
-        if self.c4_mode in ("push", "rotated") and self.active and self.world > 1:
+        if self.c4_mode in ("push", "push-flagged", "rotated") and self.active and self.world > 1:
             return (self.rank * self.block, self.world * self.block)
         return None
 
@@ -181,7 +194,7 @@ class Comm:
         """Where the producer of the NEXT SpMM operand should write its [n_local, h] block so that it needs no staging copy:
         slot 0 of that SpMM's symmetric buffer (push mode), else None (the caller allocates)."""
         esize = 2 if dtype == torch.bfloat16 else 4
-        if self.c4_mode != "push" or not self.active or self.world == 1 or (h * esize) % 16 != 0 or device.type != "cuda":
+        if self.c4_mode not in ("push", "push-flagged") or not self.active or self.world == 1 or (h * esize) % 16 != 0 or device.type != "cuda":
             return None
         st = self._push_state(h, dtype, device)
         if st is None or self._spmm_calls >= MAX_PUSH_BUFFERS:
@@ -199,21 +212,47 @@ class Comm:
             full = pad
         return torch.roll(full, shifts=-self.rank * b, dims=0)
 
-    def spmm_gathered(self, spmm, rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x_local: Tensor, heavy=None) -> Tensor:
-        """C4 + SpMM: y[rows of this rank] = scale * A[rows, :] @ (operand rows of every rank), `spmm` = kernels.spmm.
-        The CSR shard must have been built with this Comm's `col_rot`."""
+    def _spmm_phased(self, Kmod, graph, transposed: bool, rowptr, col, row_scale, buf: Tensor, wait) -> Tensor:
+        """SpMM over the rotated operand buffer in slot-group phases; wait(s0, s1) (or None) blocks the stream until slots
+        [s0, s1) have landed.  fp32 partial sums travel from phase to phase in place."""
+        groups = self.groups
+        if len(groups) == 1:
+            if wait is not None:
+                wait(1, self.world)
+            return Kmod.spmm(rowptr, col, row_scale, buf)
+        thr = tuple(g[0] * self.block for g in groups[1:])
+        sp = graph.row_splits(thr, transposed)            # int32 [G-1, n_rows], cached on the graph
+        n_rows, h = rowptr.numel() - 1, buf.shape[1]
+        part = torch.empty((n_rows, h), dtype=torch.float32, device=buf.device)
+        out = None
+        for gi, (s0, s1) in enumerate(groups):
+            if wait is not None and gi > 0:
+                wait(s0, s1)
+            last = gi == len(groups) - 1
+            out = Kmod.spmm_range(rowptr, col, row_scale, buf, sp[gi - 1] if gi > 0 else None, None if last else sp[gi],
+                                  part if gi > 0 else None, None if last else part)
+        return out
+
+    def spmm_gathered(self, Kmod, graph, transposed: bool, row_scale: Optional[Tensor], x_local: Tensor) -> Tensor:
+        """C4 + SpMM: y[rows of this rank] = scale * A[rows, :] @ (operand rows of every rank); A = `graph` (its transpose when
+        `transposed`), `Kmod` = the kernels module.  The CSR shard must have been built with this Comm's `col_rot`."""
+        rowptr, col = graph.transpose() if transposed else (graph.rowptr, graph.col)
+        heavy = graph.heavy_t if transposed else graph.heavy
+        spmm = Kmod.spmm
         if not self.active or self.world == 1:
             return spmm(rowptr, col, row_scale, x_local, heavy=heavy)
         k = self._spmm_calls
         self._spmm_calls += 1
         n_loc, h = x_local.shape
-        if self.c4_mode == "push":
-            st = self._push_state(h, x_local.dtype, x_local.device) if k < MAX_PUSH_BUFFERS else None
-            if st is not None and x_local.is_cuda:
-                return self._spmm_pushed(st, k, rowptr, col, row_scale, x_local, heavy)
-            return spmm(rowptr, col, row_scale, self._rotated_gather(x_local), heavy=heavy)
-        if self.c4_mode == "rotated":
-            return spmm(rowptr, col, row_scale, self._rotated_gather(x_local), heavy=heavy)
+        if self.c4_mode in ("push", "push-flagged"):
+            st = self._push_state(h, x_local.dtype, x_local.device) if (k < MAX_PUSH_BUFFERS and x_local.is_cuda) else None
+            if st is not None:
+                return self._spmm_pushed(st, k, Kmod, graph, transposed, rowptr, col, row_scale, x_local, heavy)
+        if self.c4_mode in ("push", "push-flagged", "rotated"):
+            buf = self._rotated_gather(x_local)
+            if heavy is not None:
+                return spmm(rowptr, col, row_scale, buf, heavy=heavy)
+            return self._spmm_phased(Kmod, graph, transposed, rowptr, col, row_scale, buf, None)
         nch = self.c4_chunks(h, x_local.element_size())
         if nch == 1:
             return spmm(rowptr, col, row_scale, self.allgather_rows(x_local), heavy=heavy)
@@ -234,8 +273,8 @@ class Comm:
             spmm(rowptr, col, row_scale, gc[:self.n_global], out=out[:, c * hc:(c + 1) * hc], heavy=heavy)
         return out
 
-    def _spmm_pushed(self, st: _PushState, k: int, rowptr, col, row_scale, x_local: Tensor, heavy) -> Tensor:
-        from . import kernels as K
+    def _spmm_pushed(self, st: _PushState, k: int, Kmod, graph, transposed, rowptr, col, row_scale, x_local: Tensor, heavy) -> Tensor:
+        K = Kmod
         w, b, rank = self.world, self.block, self.rank
         buf, peers = st.buffer(k)
         n_loc = x_local.shape[0]
@@ -251,16 +290,24 @@ class Comm:
                 r = (rank - s) % w
                 K.memcpy_async(peers[r][s * b:s * b + n_loc], own)               # copy-engine peer copy over NVLink
                 # ... and the arrival flag behind it, ALSO by the copy engine: a 1-thread flag kernel of another stream is never
-                # scheduled while the consumer's flagged SpMM holds the SMs spinning (measured on B200: tests/push_debug2.py stages
-                # S1/P2 trap, S2/P1 pass), whereas stream-ordered copy-engine writes need no SM
+                # scheduled while a consumer kernel holds the SMs spinning on that flag (measured on B200: tests/push_debug2.py
+                # stages S1/P2 trap, S2/P1 pass), whereas stream-ordered copy-engine writes need no SM
                 K.memcpy_async(st.peer_flags[r][k, s:s + 1], st.one)
             done = torch.cuda.Event()
             done.record(st.side)
-        y = K.spmm_flagged(rowptr, col, row_scale, buf, st.flags[k], b, heavy=heavy)
+        flags = st.flags[k]
+        if self.c4_mode == "push-flagged" or heavy is not None:
+            if heavy is not None:
+                K.wait_flags(flags[1:])
+                y = K.spmm(rowptr, col, row_scale, buf, heavy=heavy)
+            else:
+                y = K.spmm_flagged(rowptr, col, row_scale, buf, flags, b)
+        else:
+            y = self._spmm_phased(K, graph, transposed, rowptr, col, row_scale, buf, lambda s0, s1: K.wait_flags(flags[s0:s1]))
         # every peer's signal of THIS use has been seen before the flags are lowered for the next step (a slot no row references
         # would otherwise leave a late signal behind); the step's collectives (C1 / C5) order the reuse of the buffer itself
-        K.wait_flags(st.flags[k, 1:])
-        st.flags[k].zero_()
+        K.wait_flags(flags[1:])
+        flags.zero_()
         main.wait_event(done)
         return y
 

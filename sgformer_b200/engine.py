@@ -509,7 +509,7 @@ def gconv_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, t
     out = x0
     for i in range(nl):
         last = i == nl - 1
-        y = comm.spmm_gathered(K.spmm, graph.rowptr, graph.col, dinv, cur_s, heavy=graph.heavy)    # C4: operand rows of every shard
+        y = comm.spmm_gathered(K, graph, False, dinv, cur_s)    # C4: operand rows of every shard
         st = _stat_bufs(use_bn, training, h, dev)      # BatchNorm sums come out of the GEMM epilogue
         if use_init:
             w = _w(P, f"{pfx}convs.{i}.W.weight", prec)
@@ -595,7 +595,7 @@ def gconv_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: P
         else:
             dys = K.axpby(dz, None, 1.0, 0.0, row_scale=dinv, out=comm.operand_out(n, h, prec.act_dtype, dev))
         # = A^T (dinv . dy): gradient w.r.t. the pre-scaled SpMM input (C4: gradient rows of every shard)
-        dy_scaled = comm.spmm_gathered(K.spmm, rowptr_t, col_t, None, dys, heavy=graph.heavy_t)
+        dy_scaled = comm.spmm_gathered(K, graph, True, None, dys)
         dy_plain = None
     # input layer epilogue: gradient of x0 = accumulated dx0 (+ dinv * dy_scaled from layer 0's SpMM)
     if nl == 0:
@@ -664,7 +664,7 @@ def gcn_forward(P, cfg: dict, xin: K.Operand, graph: Graph, prec: Precision, tra
         check_width(hout, prec, f"GCN layer {i} out_channels")
         t = K.gemm_nt([cur_op], [_w(P, wname, prec)], [(0, 0, 0, 0, cur_k)], hout, K.alloc_act(n, hout, prec.act_dtype, dev),
                       row_scale=dinv)
-        s = comm.spmm_gathered(K.spmm, graph.rowptr, graph.col, dinv, t, heavy=graph.heavy)
+        s = comm.spmm_gathered(K, graph, False, dinv, t)
         zb = P.get(f"{pfx}convs.{i}.bias")
         if last:
             out, _ = K.bn_fwd(s, None, mix, None, None, None, None, zb, False, False, 0.0, 0, gw, None, True, False)
@@ -713,7 +713,7 @@ def gcn_backward(P, cfg: dict, tape: Tape, graph: Graph, dout: Tensor, prec: Pre
         gs = 1.0
         if zb is not None:
             grads[f"{pfx}convs.{i}.bias"] = colsum
-        u = comm.spmm_gathered(K.spmm, rowptr_t, col_t, dinv, dzs, heavy=graph.heavy_t)        # = Â^T dz = gradient of (x W^T)
+        u = comm.spmm_gathered(K, graph, True, dinv, dzs)        # = Â^T dz = gradient of (x W^T)
         u_op = K.as_operand(u, prec.planes)
         wname = f"{pfx}convs.{i}.lin.weight"
         dw = torch.empty((hout, L["cur_k"]), dtype=torch.float32, device=dev)

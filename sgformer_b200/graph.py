@@ -76,6 +76,17 @@ class Graph:
         g.nnz_needed, g.capacity = needed, capacity      # device int64 [1]: > capacity means the batch structure was truncated
         return g
 
+    def row_splits(self, thresholds: Tuple[int, ...], transposed: bool = False) -> Tensor:
+        """int32 [len(thresholds), n_rows]: per row the number of entries whose (rotated) column id is below each threshold - the
+        phase boundaries of a row-sharded SpMM (dist.Comm._spmm_phased); cached."""
+        rp, cl = self.transpose() if transposed else (self.rowptr, self.col)
+        same = rp is self.rowptr
+        key = (tuple(thresholds), transposed and not same)
+        cache = self.__dict__.setdefault("_splits", {})
+        if key not in cache:
+            cache[key] = K.csr_row_splits(rp, cl, thresholds)
+        return cache[key]
+
     def transpose(self) -> Tuple[Tensor, Tensor]:
         """CSR of the transposed pattern (rows = edge sources) for the backward SpMM; shares storage when the edge
         list is symmetric (the usual case after to_undirected)."""

@@ -299,6 +299,44 @@ def spmm_flagged(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Te
     return out
 
 
+def csr_row_splits(rowptr: Tensor, col: Tensor, thresholds: Sequence[int]) -> Tensor:
+    """int32 [len(thresholds), n_rows]: per row the number of entries with column id < threshold (rows sorted by column)."""
+    _use(rowptr)
+    n = rowptr.numel() - 1
+    thr = torch.tensor(list(thresholds), dtype=torch.int32, device=rowptr.device)
+    out = torch.empty((len(thresholds), max(n, 1)), dtype=torch.int32, device=rowptr.device)
+    check(lib().sgf_csr_row_splits(_p(rowptr), _p(col), n, _p(thr), len(thresholds), _p(out), _stream()), "sgf_csr_row_splits")
+    return out[:, :n]
+
+
+def spmm_range(rowptr: Tensor, col: Tensor, row_scale: Optional[Tensor], x: Tensor, lo: Optional[Tensor], hi: Optional[Tensor],
+               part_in: Optional[Tensor], part_out: Optional[Tensor]) -> Optional[Tensor]:
+    """One phase of a phased SpMM (sgf_spmm_range): entries [lo, hi) of every row, plus part_in, into part_out (fp32 partials;
+    returns None) or, when part_out is None, scaled into a new activation that is returned."""
+    _use(x)
+    n = rowptr.numel() - 1
+    _, h, ldx = _mat(x, "x")
+    ev = spmm_events
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    out = alloc_act(n, h, x.dtype, x.device) if part_out is None else None
+    ldp = (part_in if part_in is not None else part_out).stride(0) if (part_in is not None or part_out is not None) else 0
+    for t in (lo, hi):
+        if t is not None and (t.dtype != torch.int32 or not t.is_contiguous() or t.numel() < n):
+            raise ValueError("spmm_range: lo / hi must be contiguous int32 [n_rows]")
+    for t in (part_in, part_out):
+        if t is not None and (t.dtype != torch.float32 or t.stride(1) != 1 or t.shape[0] < n or t.shape[1] != h):
+            raise ValueError("spmm_range: partials must be fp32 [n_rows, h]")
+    rs = _f32vec(row_scale, n, "row_scale") if part_out is None else None
+    check(lib().sgf_spmm_range(_p(rowptr), _p(col), _p(rs), _p(x), ldx, _p(out), out.stride(0) if out is not None else 0, n, h,
+                               dcode(x), _p(lo), _p(hi), _p(part_in), _p(part_out), ldp, _stream()), "sgf_spmm_range")
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1))
+    return out
+
+
 def memcpy_async(dst: Tensor, src: Tensor):
     """Stream-ordered raw copy src -> dst (same byte size, both contiguous) on the current stream; dst may be the mapping of a
     peer GPU's symmetric buffer (sgf_memcpy_async: copy engine over NVLink, no cross-device stream synchronisation)."""

@@ -78,6 +78,36 @@ def spmm(rowptr, col, row_scale, x, out=None, heavy=None):
     return _st(out if out is not None else alloc_act(n, x.shape[1], x.dtype, x.device), y)
 
 
+def csr_row_splits(rowptr, col, thresholds):
+    n = rowptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    out = torch.zeros((len(thresholds), n), dtype=torch.int32)
+    for t, thr in enumerate(thresholds):
+        out[t] = torch.zeros(n, dtype=torch.int64).index_add_(0, rows, (col.long() < thr).long()).to(torch.int32)
+    return out
+
+
+def spmm_range(rowptr, col, row_scale, x, lo, hi, part_in, part_out):
+    n = rowptr.numel() - 1
+    lens = rowptr[1:] - rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n), lens)
+    pos = torch.arange(col.numel()) - rowptr[:-1][rows]
+    keep = torch.ones(col.numel(), dtype=torch.bool)
+    if lo is not None:
+        keep &= pos >= lo.long()[rows]
+    if hi is not None:
+        keep &= pos < hi.long()[rows]
+    acc = torch.zeros((n, x.shape[1]), dtype=torch.float32).index_add_(0, rows[keep], x.float()[col.long()[keep]])
+    if part_in is not None:
+        acc = acc + part_in
+    if part_out is not None:
+        part_out.copy_(acc)
+        return None
+    if row_scale is not None:
+        acc = acc * row_scale[:, None]
+    return _st(alloc_act(n, x.shape[1], x.dtype, x.device), acc)
+
+
 def operand_from_bf16(x):
     return Operand(x.float(), x.shape[0], x.shape[1], x.shape[1], 1)
 
@@ -439,5 +469,11 @@ class EmuGraph:
         self.heavy = self.heavy_t = None
 
     def transpose(self):
-        rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows, col_rot=self.col_rot)
-        return rp, cl
+        if not hasattr(self, "_t"):
+            rp, cl, _ = csr_build(self.edge_index, self.n, True, self.self_loop_mode, False, rows=self.rows, col_rot=self.col_rot)
+            self._t = (rp, cl)
+        return self._t
+
+    def row_splits(self, thresholds, transposed=False):
+        rp, cl = self.transpose() if transposed else (self.rowptr, self.col)
+        return csr_row_splits(rp, cl, thresholds)

@@ -55,15 +55,21 @@ def main():
                 gerr, worst = e, k
         good = err <= tol and gerr <= (1e-3 if prec == "fp32" else 5e-2)
         ok = ok and good
-        if rank == 0:
-            print(f"[{prec}] world={world}: logits rel err {err:.3e}, worst parameter-grad rel err {gerr:.3e} ({worst}) -> {'OK' if good else 'FAIL'}")
+        if rank == 0 or not good:
+            print(f"[{prec}] rank {rank} world={world}: logits rel err {err:.3e}, worst parameter-grad rel err {gerr:.3e} ({worst}) -> {'OK' if good else 'FAIL'}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    dist.destroy_process_group()
-    if flag.item() != 1:
-        sys.exit(1)
+    passed = flag.item() == 1
     if rank == 0:
-        print("multi_gpu_check: OK")
+        print("multi_gpu_check: OK" if passed else "multi_gpu_check: FAILED", flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    del shard, ref, comm          # symmetric buffers go before the process group they were rendezvoused on
+    import gc
+    gc.collect()
+    dist.destroy_process_group()
+    if not passed:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -775,3 +775,30 @@ def test_gram_kernel(K, monkeypatch, rows, h, planes):
     Gl, sl = K.gram(X, xd)          # colstats of the fp32 rows: the bf16 plane rounds each element by <= 2^-9
     _close(G, Gl, tol, tol * rows ** 0.5, "dedicated kernel vs gemm_tn path")
     _close(s, sl, tol, tol * rows ** 0.5, "s vs colstats path")
+
+
+@pytest.mark.parametrize("dtype,h", [(torch.bfloat16, 256), (torch.bfloat16, 64), (torch.float32, 128), (torch.float32, 100)])
+def test_spmm_range_phases_equal_the_whole(K, dtype, h):
+    """Rotated CSR + sgf_csr_row_splits + sgf_spmm_range: running the slot-group phases one after the other (fp32 partials carried
+    in place) gives the plain SpMM of the same rows; splits are exact."""
+    n, world, rank = 9001, 4, 1
+    block = (n + world - 1) // world
+    r0, r1 = rank * block, min(n, (rank + 1) * block)
+    ei = rand_graph(n, 60000, 7)
+    rp, cl, dinv = K.csr_build(ei.to(DEV), n, rows=(r0, r1), col_rot=(r0, world * block))
+    rpe, cle, dve = emu.csr_build(ei, n, rows=(r0, r1), col_rot=(r0, world * block))
+    assert torch.equal(rp.cpu(), rpe) and torch.equal(cl.cpu(), cle), "rotated CSR differs from its definition"
+    thr = (block, 2 * block, 3 * block)
+    sp = K.csr_row_splits(rp, cl, thr)
+    assert torch.equal(sp.cpu(), emu.csr_row_splits(rpe, cle, thr))
+    x = torch.randn(world * block, h, generator=torch.Generator().manual_seed(3)).to(dtype).to(DEV)
+    whole = K.spmm(rp, cl, dinv, x)
+    part = torch.empty((r1 - r0, h), dtype=torch.float32, device=DEV)
+    K.spmm_range(rp, cl, dinv, x, None, sp[0], None, part)
+    K.spmm_range(rp, cl, dinv, x, sp[0], sp[1], part, part)
+    K.spmm_range(rp, cl, dinv, x, sp[1], sp[2], part, part)
+    out = K.spmm_range(rp, cl, dinv, x, sp[2], None, part, None)
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    _close(out.float(), whole.float(), tol, tol, "phased SpMM vs single launch")
+    ref = emu.spmm(rpe, cle, dve, x.cpu())
+    _close(out.float(), ref.float(), 2e-5 if dtype == torch.float32 else 2e-2, 1e-5, "phased SpMM vs contract")

@@ -26,4 +26,7 @@ def test_row_sharded_nccl_matches_single_gpu(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "multi_gpu_check: OK" in r.stdout, (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
+    info = "\n".join(ln for ln in (r.stdout + "\n" + r.stderr).splitlines()
+                     if any(t in ln for t in ("rel err", "multi_gpu_check", "Error", "error", "Traceback", "File \"/root")))[-4000:]
+    assert "multi_gpu_check: OK" in r.stdout, info
+    assert r.returncode == 0, "checks passed but a rank exited with an error (teardown):\n" + info
