@@ -114,7 +114,8 @@ class Comm:
         self.c4_mode = mode
         # slot groups of the phased SpMM: every slot its own phase up to 4 GPUs, else the local slot + 3 groups of remote slots
         # (each phase boundary costs one fp32 write + read of the partial sums, each group delays its slots to the last arrival)
-        ng = int(os.environ.get("SGF_C4_GROUPS", "0")) or min(self.world, 4)
+        self._groups_forced = int(os.environ.get("SGF_C4_GROUPS", "0"))
+        ng = self._groups_forced or min(self.world, 4)
         ng = max(1, min(ng, self.world))
         if ng == 1:
             self.groups = [(0, self.world)]
@@ -296,7 +297,11 @@ class Comm:
             done = torch.cuda.Event()
             done.record(st.side)
         flags = st.flags[k]
-        if self.c4_mode == "push-flagged" or heavy is not None:
+        # phased vs in-row waiting (measured, profiles/r2_scaling.md): the phases pay one fp32 write + read of the partial sums per
+        # boundary and shorter per-row gathers, the in-row wait overlaps nothing; phases win for 512-byte rows from 4 GPUs on
+        # (products 29.9 vs 30.9 ms at 4), the single flagged launch for 128-byte rows (Pokec 4.56 vs 5.67 ms at 4) and at 2 GPUs
+        phased = self._groups_forced > 1 or (self._groups_forced == 0 and w >= 4 and x_local.shape[1] * x_local.element_size() >= 512)
+        if self.c4_mode == "push-flagged" or heavy is not None or not phased:
             if heavy is not None:
                 K.wait_flags(flags[1:])
                 y = K.spmm(rowptr, col, row_scale, buf, heavy=heavy)
