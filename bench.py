@@ -228,7 +228,8 @@ class Ctx:
         if self.world > 1:
             import torch.distributed as dist
             import datetime
-            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=300))
+            dist.init_process_group("nccl", device_id=self.dev,
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("SGF_BENCH_INIT_TIMEOUT", "300"))))
             self.dist = dist
 
     def barrier(self):
@@ -576,7 +577,10 @@ def extras_in_children(ctx, args):
     torch.cuda.empty_cache()
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 23)
-    env.pop("TORCHELASTIC_RUN_ID", None)
+    for k in list(env):          # without torchrun's agent store the children's rank 0 hosts its own TCPStore on the new port
+        if k.startswith("TORCHELASTIC_"):
+            env.pop(k)
+    env["SGF_BENCH_INIT_TIMEOUT"] = "120"
     cmd = [sys.executable, os.path.abspath(__file__), "--extras-child", "--gpus", str(args.gpus), "--steps", str(args.steps),
            "--warmup", str(args.warmup)]
     out = None

@@ -6,6 +6,16 @@ timeout 1500 python -m pytest tests -q -m gpu --durations=5 > $OUT/all_gpu.log 2
 grep -E "passed|failed" $OUT/all_gpu.log; grep -E "^(FAILED|E   [A-Za-z])" $OUT/all_gpu.log | cut -c1-300 | head -30
 timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > $OUT/bench_default.log 2>&1; echo "bench rc=$?"
 grep "^{" $OUT/bench_default.log | cut -c1-4000
+# the vectorised operand-pack kernel (fp32 / bf16x3 path), never run on a GPU in r1: validate it and measure it
+SGF_PACK_VEC=1 timeout 900 python -m pytest tests -q -m gpu -k "pack_operand or gemm_nt or gemm_tn or golden or arxiv or midsize or gram" > $OUT/pack_vec_tests.log 2>&1; echo "pytest with SGF_PACK_VEC=1 rc=$?"
+grep -E "passed|failed" $OUT/pack_vec_tests.log
+for PV in 0 1; do
+  SGF_PACK_VEC=$PV timeout 300 python bench.py --workload arxiv --no-cpu-baseline --no-e2e --no-extra --steps 30 --warmup 5 > $OUT/bench_arxiv_pv$PV.log 2>&1
+  grep "^{" $OUT/bench_arxiv_pv$PV.log | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('arxiv fp32 SGF_PACK_VEC=$PV ms/step', d['ms_per_step'])"
+done
 B="python bench.py --no-cpu-baseline --no-e2e --no-extra --no-graph"
 # skip the warm-up steps' launches: full metric set of every instance of the attention kernels in the timed step
 for KN in gram_kernel ln_bwd_attn_kernel; do
