@@ -580,7 +580,7 @@ def extras_in_children(ctx, args):
     for k in list(env):          # without torchrun's agent store the children's rank 0 hosts its own TCPStore on the new port
         if k.startswith("TORCHELASTIC_"):
             env.pop(k)
-    env["SGF_BENCH_INIT_TIMEOUT"] = "120"
+    env["SGF_BENCH_INIT_TIMEOUT"] = "240"
     cmd = [sys.executable, os.path.abspath(__file__), "--extras-child", "--gpus", str(args.gpus), "--steps", str(args.steps),
            "--warmup", str(args.warmup)]
     out = None

@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 N=${1:-2}
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 if [ "${SKIP_MULTI:-0}" != "1" ]; then timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu > $OUT/multi_pytest_$N.log 2>&1; echo "pytest multi rc=$?"; grep -E "passed|failed|skipped" $OUT/multi_pytest_$N.log; fi
-timeout 1500 $T bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench_driver_$N.log 2> $OUT/bench_driver_$N.err; echo "bench --gpus $N rc=$?"
+timeout 1500 $T bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 ${BENCH_FLAGS:-} > $OUT/bench_driver_$N.log 2> $OUT/bench_driver_$N.err; echo "bench --gpus $N rc=$?"
 grep "^{" $OUT/bench_driver_$N.log | python -c "
 import sys,json
 for l in sys.stdin:
