@@ -510,8 +510,17 @@ def extras(ctx, args):
     world, rank = ctx.world, ctx.rank
     st, wu = max(3, min(args.steps, 10)), 3
     out = {}
+    t_begin = time.perf_counter()
+    budget = float(os.environ.get("SGF_BENCH_EXTRA_BUDGET", "330"))      # seconds: later items are skipped, never cut short
 
     def guard(name, fn):
+        # every rank takes the same decision (rank 0's clock)
+        over = torch.tensor([1 if time.perf_counter() - t_begin > budget else 0], device=ctx.dev)
+        if ctx.dist is not None:
+            ctx.dist.broadcast(over, 0)
+        if int(over.item()):
+            out[name] = {"skipped": f"extra-measurement time budget of {budget:.0f} s used up"}
+            return
         try:
             out[name] = fn()
         except Exception as exc:  # one failing extra must not take the headline line down
@@ -585,7 +594,7 @@ def extras_in_children(ctx, args):
            "--warmup", str(args.warmup)]
     out = None
     try:
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=720)
         for ln in r.stdout.splitlines():
             if ln.startswith("EXTRAS_JSON "):
                 out = json.loads(ln[len("EXTRAS_JSON "):])
