@@ -298,9 +298,11 @@ class Comm:
             done.record(st.side)
         flags = st.flags[k]
         # phased vs in-row waiting (measured, profiles/r2_scaling.md): the phases pay one fp32 write + read of the partial sums per
-        # boundary and shorter per-row gathers, the in-row wait overlaps nothing; phases win for 512-byte rows from 4 GPUs on
-        # (products 29.9 vs 30.9 ms at 4), the single flagged launch for 128-byte rows (Pokec 4.56 vs 5.67 ms at 4) and at 2 GPUs
-        phased = self._groups_forced > 1 or (self._groups_forced == 0 and w >= 4 and x_local.shape[1] * x_local.element_size() >= 512)
+        # boundary and shorter per-row gathers, the in-row wait overlaps nothing.  ms/step, phased vs flagged: products (512-byte
+        # rows) 49.8 / 49.7 at 2 GPUs, 29.9 / 30.9 at 4, 17.6 / 21.6 at 8; Pokec (128-byte rows) 7.8 / 7.1 at 2, 5.7 / 4.6 at 4,
+        # 3.4 / 3.5 at 8
+        rowbytes = x_local.shape[1] * x_local.element_size()
+        phased = self._groups_forced > 1 or (self._groups_forced == 0 and ((w >= 4 and rowbytes >= 512) or w >= 8))
         if self.c4_mode == "push-flagged" or heavy is not None or not phased:
             if heavy is not None:
                 K.wait_flags(flags[1:])
