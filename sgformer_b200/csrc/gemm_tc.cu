@@ -1002,7 +1002,18 @@ extern "C" int sgf_gemm_nt(const sgf_gemm_nt_args* a, void* stream) {
     p.n_blocks = (n16 + 255) / 256;
     // a 16-column tail needs n-block + 16 <= 256 TMEM columns per accumulator stage to keep the two stages (MMA of tile i+1
     // overlapping the epilogue of tile i): split a 256-wide output into two 128(+16) blocks (the tail is recomputed, cheap)
-    if (has_tail && n16 + 16 > 256) p.n_blocks = 2;
+    // ... unless the whole B (all k-blocks of the 256 + 16 columns) can stay resident in shared memory: then ONE n-block with a
+    // single 272-column accumulator stage reads A once and B never again (the split form re-reads the A tile and re-streams 73 KB of
+    // B per 128 x 128 output tile: 5.2 GB through L2 for the 1.25 GB attention apply at the products shape, 0.76 ms, L2-bound).
+    bool tail_one_block = false;
+    if (has_tail && n16 + 16 > 256) {
+        static const bool res_ok = [] { const char* e = getenv("SGF_ATTN_RESIDENT"); return !(e && e[0] == '0'); }();
+        int kb = 0;
+        for (int s = 0; s < a->n_seg; ++s) kb += (a->seg_klen[s] + nt::BK - 1) / nt::BK;
+        tail_one_block = res_ok && a->schedule != SGF_GEMM_STREAM_B && n16 <= 256 && kb <= nt::RES_MAX_KB &&
+                         (int64_t)(n16 + 16) * nt::BK * 2 * kb <= nt::RES_BYTES;
+        if (!tail_one_block) p.n_blocks = 2;
+    }
     // equal-width n-blocks: a multiple of 16 (UMMA N), and of 64 when there are several - the epilogue stores 128-byte
     // groups (64 bf16 / 32 fp32 columns), which must not reach into the next n-block's columns
     p.bn_main = p.n_blocks == 1 ? n16 : ((n16 / p.n_blocks + 63) / 64) * 64;
