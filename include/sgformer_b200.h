@@ -393,6 +393,13 @@ typedef struct {
 int sgf_attn_gram_ws_floats(int h, int m, int d, int64_t* n_floats /* host out */);
 int sgf_attn_gram_prepare_fwd(const sgf_attn_gram_args* args /* host */, void* stream);
 int sgf_attn_gram_prepare_bwd(const sgf_attn_gram_args* args /* host */, void* stream);
+/* Dropout epoch.  Every kernel that takes (p, seed) draws its mask from hash(seed + epoch * odd, row, chunk); `epoch` is read from
+ * the device word registered here (NULL, the default: epoch 0).  The host seed of a call is frozen into a captured CUDA graph;
+ * a step that is captured and replayed registers an epoch word and puts sgf_advance_dropout_epoch at the top of the captured
+ * step, so that every replay draws fresh masks while forward and backward of one step still agree (F.dropout semantics,
+ * large/ours.py:216).  One word per process (one process per GPU). */
+int sgf_set_dropout_epoch(const uint64_t* epoch_dev /* device, stays alive; NULL to unregister */);
+int sgf_advance_dropout_epoch(uint64_t* epoch_dev, void* stream);   /* *epoch_dev += 1 on the stream */
 /* LayerNorm backward of y = dropout(relu?(LN?(a*o + b*r))) (TransConv.forward, large/ours.py:208-216) fused with the row
  * prologue of the attention backward: with du the gradient w.r.t. u = a*o + b*r (as sgf_ln_bwd) and ga = a*du,
  *   gnum[r,:] = ga/den[r],  gden[r] = -(ga . o[r,:])/den[r],  dr (nullable) = b*du,

@@ -102,6 +102,8 @@ _SIGS = {
     "sgf_spmm_range": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sgf_csr_row_splits": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, _vp, _vp]),
     "sgf_signal": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "sgf_set_dropout_epoch": (C.c_int, [_vp]),
+    "sgf_advance_dropout_epoch": (C.c_int, [_vp, _vp]),
     "sgf_memcpy_async": (C.c_int, [_vp, _vp, _sz, _vp]),
     "sgf_wait_flags": (C.c_int, [_vp, C.c_int, _vp]),
     "sgf_csr_build_rot": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),

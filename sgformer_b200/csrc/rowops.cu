@@ -19,6 +19,19 @@ namespace sgf {
 constexpr int kRowBlock = 256;
 constexpr float kLnEps = 1e-5f;
 
+// Dropout seed as the kernels receive it: the host seed of the call plus an optional device-resident epoch word
+// (sgf_set_dropout_epoch).  A step captured in a CUDA graph bakes the host seed into the graph; the epoch, advanced by a
+// node of the same graph, is what makes every replay draw fresh masks (forward and backward of one step read the same value).
+static const uint64_t* g_dropout_epoch = nullptr;
+struct SeedArg {
+    uint64_t base;
+    const uint64_t* epoch;
+    SeedArg(uint64_t s) : base(s), epoch(g_dropout_epoch) {}
+    __device__ __forceinline__ uint64_t get() const {
+        return epoch ? base + (*epoch) * 0xD1B54A32D192ED03ULL : base;
+    }
+};
+
 struct RowGeom {
     int chunks, lpr_log2, cpl;
 };
@@ -192,8 +205,9 @@ template <typename T, int CPL, bool DROP>
 __global__ void __launch_bounds__(kRowBlock, 3) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ rr, int64_t ld, int64_t rows,
                                                             int h, int chunks, int lpr_log2, float a, float b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int use_ln,
-                                                            int use_relu, float p, uint64_t seed, T* __restrict__ y,
+                                                            int use_relu, float p, SeedArg seed_arg, T* __restrict__ y,
                                                             float* __restrict__ stats) {
+    const uint64_t seed = DROP ? seed_arg.get() : 0;
     constexpr int VN = Vec16<T>::N;
     Lane<T, CPL> L(chunks, lpr_log2);
     float g[CPL][VN], be[CPL][VN];
@@ -257,8 +271,9 @@ __global__ void __launch_bounds__(kRowBlock, 3) ln_bwd_kernel(const T* __restric
                                                             int64_t ld, int64_t rows, int h, int chunks, int lpr_log2, float a, float b,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ stats, int use_ln, int use_relu, float p,
-                                                            uint64_t seed, float gscale, T* __restrict__ dx, T* __restrict__ dr,
+                                                            SeedArg seed_arg, float gscale, T* __restrict__ dx, T* __restrict__ dr,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const uint64_t seed = DROP ? seed_arg.get() : 0;
     constexpr int VN = Vec16<T>::N;
     extern __shared__ float sm[];
     Lane<T, CPL> L(chunks, lpr_log2);
@@ -355,11 +370,12 @@ __global__ void __launch_bounds__(kRowBlock, (CPL >= 2 ? 1 : MINB)) ln_bwd_attn_
                                                                     const T* __restrict__ xa, int64_t ld, int64_t rows, int h, int chunks,
                                                                     int lpr_log2, float a, float b, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, const float* __restrict__ stats,
-                                                                    int use_ln, float p, uint64_t seed, float gscale,
+                                                                    int use_ln, float p, SeedArg seed_arg, float gscale,
                                                                     const float* __restrict__ den, T* __restrict__ gnum,
                                                                     float* __restrict__ gden, T* __restrict__ dr,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                     float* __restrict__ cs, float* __restrict__ pg, float* __restrict__ sg) {
+    const uint64_t seed = DROP ? seed_arg.get() : 0;
     constexpr int VN = Vec16<T>::N;
     extern __shared__ float sm[];
     Lane<T, CPL> L(chunks, lpr_log2);
@@ -507,9 +523,10 @@ __global__ void __launch_bounds__(kRowBlock, 3) bn_fwd_kernel(const T* __restric
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ zbias, int use_bn,
-                                                            int use_relu, float p, uint64_t seed, float gw,
+                                                            int use_relu, float p, SeedArg seed_arg, float gw,
                                                             const float* __restrict__ row_scale, T* __restrict__ y,
                                                             T* __restrict__ y_scaled) {
+    const uint64_t seed = DROP ? seed_arg.get() : 0;
     constexpr int VN = Vec16<T>::N;
     Lane<T, CPL> L(chunks, lpr_log2);
     float sc[CPL][VN], sh[CPL][VN];
@@ -565,11 +582,12 @@ __global__ void __launch_bounds__(kRowBlock, 2) bn_bwd_kernel(const T* __restric
                                                                int64_t rows, int h, int chunks, int lpr_log2, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, const float* __restrict__ zbias, int use_bn,
-                                                               int use_relu, int training, float p, uint64_t seed, float gscale,
+                                                               int use_relu, int training, float p, SeedArg seed_arg, float gscale,
                                                                int64_t stat_rows, float* __restrict__ sums, T* __restrict__ dz,
                                                                T* __restrict__ dres,
                                                                int dres_acc, float* __restrict__ dz_colsum,
                                                                const float* __restrict__ out_scale) {
+    const uint64_t seed = DROP ? seed_arg.get() : 0;
     constexpr int VN = Vec16<T>::N;
     extern __shared__ float sm[];
     Lane<T, CPL> L(chunks, lpr_log2);
@@ -1331,5 +1349,22 @@ extern "C" int sgf_eval_acc(const float* logits, int64_t ld, const int64_t* labe
     eval_acc_kernel<<<(unsigned)blocks, kRowBlock, 0, st>>>(logits, ld, labels, idx, m, rows, c,
                                                             reinterpret_cast<unsigned long long*>(correct), nll_sum);
     SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+// Device-resident dropout epoch (see SeedArg).
+namespace sgf {
+__global__ void advance_epoch_kernel(uint64_t* e) { *e += 1; }
+}  // namespace sgf
+
+extern "C" int sgf_set_dropout_epoch(const uint64_t* epoch_dev) {
+    sgf::g_dropout_epoch = epoch_dev;
+    return SGF_OK;
+}
+
+extern "C" int sgf_advance_dropout_epoch(uint64_t* epoch_dev, void* stream) {
+    if (!epoch_dev) return SGF_ERR_ARG;
+    sgf::advance_epoch_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch_dev);
+    SGF_LAUNCH_CHECK(); sgf::count_launch();
     return SGF_OK;
 }

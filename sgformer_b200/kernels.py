@@ -352,6 +352,24 @@ def wait_flags(flags: Tensor):
         check(lib().sgf_wait_flags(_p(flags), flags.numel(), _stream()), "sgf_wait_flags")
 
 
+_epoch = None
+
+
+def dropout_epoch(create: bool = True):
+    """The device word the dropout kernels add to their seed (sgf_set_dropout_epoch); created and registered on first use."""
+    global _epoch
+    if _epoch is None and create:
+        _epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+        check(lib().sgf_set_dropout_epoch(_p(_epoch)), "sgf_set_dropout_epoch")
+    return _epoch
+
+
+def advance_dropout_epoch():
+    """*epoch += 1 on the current stream: call once at the top of a training step that is captured in a CUDA graph, so that
+    every replay draws fresh dropout masks (the host seed is frozen into the graph)."""
+    check(lib().sgf_advance_dropout_epoch(_p(dropout_epoch()), _stream()), "sgf_advance_dropout_epoch")
+
+
 def signal(flag: Tensor, value: int = 1):
     """flag[0] = value (release, system scope) on the current stream; `flag` may be a view of a peer GPU's symmetric memory."""
     check(lib().sgf_signal(_p(flag), value, _stream()), "sgf_signal")

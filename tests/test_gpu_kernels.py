@@ -388,6 +388,34 @@ def test_dropout_statistics_and_consistency(K):
     assert abs((yb > 0).float().mean().item() - (1 - p)) < 0.01 and torch.equal(dz > 0, yb > 0)
 
 
+def test_dropout_epoch_under_graph_replay(K):
+    """A captured step freezes the host seed; the device epoch (sgf_advance_dropout_epoch inside the graph) must give every
+    replay fresh masks while the backward of the same replay recomputes the forward's mask (dropout seed)."""
+    n, h, p = 2048, 64, 0.4
+    x = torch.ones(n, h, device=DEV)
+    K.dropout_epoch()                       # registers the word
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        K.advance_dropout_epoch()           # warm-up outside the capture
+        K.ln_fwd(x, None, 1.0, 0.0, None, None, False, False, p, 99)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        K.advance_dropout_epoch()
+        y, _ = K.ln_fwd(x, None, 1.0, 0.0, None, None, False, False, p, 99)
+        dx, _ = K.ln_bwd(x, x, None, 1.0, 0.0, None, None, None, False, False, p, 99, 1.0, False, None, None)
+    masks = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(dx > 0, y > 0), "forward / backward masks of one replay differ"
+        assert abs((y > 0).float().mean().item() - (1 - p)) < 0.02
+        masks.append((y > 0).clone())
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert abs((masks[0] & masks[1]).float().mean().item() - (1 - p) ** 2) < 0.02, "masks of consecutive replays are correlated"
+
+
 def test_softmax_nll_matches_torch(K):
     from sgformer_b200.loss import nll_loss_from_logits
     g = torch.Generator().manual_seed(4)
