@@ -73,6 +73,7 @@ class _PushState:
         # flagged SpMM spins on this very rank's push).
         from . import kernels as K
         K._use(self.flags)
+        self.fence = torch.zeros(1, dtype=torch.float32, device=device)
         self.one = torch.ones(1, dtype=torch.int32, device=device)     # source of the arrival flags (copied by the copy engine)
         for r in range(w):
             if r != comm.rank:
@@ -125,6 +126,8 @@ class Comm:
             self.groups = [(0, 1)] + [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
         self._push = {}            # (h, dtype) -> _PushState
         self._spmm_calls = 0       # position of the next SpMM inside the current step (selects the symmetric buffer)
+        self._coll_seq = 0         # collectives issued through this Comm so far
+        self._last_use = {}        # symmetric buffer k -> _coll_seq after its last use (see _fence_reuse)
         self._push_failed = False
 
     # column-id rotation the CSR shard of this rank must be built with (None: global ids)
@@ -138,12 +141,22 @@ class Comm:
         """Called at the start of every sharded forward: SpMM k of this step uses symmetric buffer k."""
         self._spmm_calls = 0
 
+    def _fence_reuse(self, st, k: int):
+        """Symmetric buffer k may be overwritten by a peer's push of the NEXT use as soon as that peer gets there, so a collective
+        that every rank joins only after finishing its previous read of buffer k has to lie between two uses.  The step's own
+        all-reduces (C1 Gram, C3 BatchNorm) normally are that collective; a schedule without any (no attention layer, eval mode,
+        one GCN layer) gets an explicit 4-byte all-reduce here.  Every rank runs the same schedule, so all take the same branch."""
+        if self._last_use.get(k) == self._coll_seq:
+            dist.all_reduce(st.fence, group=self.group)
+            self._coll_seq += 1
+
     # -- small reductions (C1, C2, C3, C5) ----------------------------------------------------------
     def allreduce_(self, *tensors: Tensor):
         """In-place sum over ranks; several small fp32 tensors travel as one flat buffer."""
         if not self.active or self.world == 1:
             return
         ts = [t for t in tensors if t is not None]
+        self._coll_seq += 1
         if len(ts) == 1 and ts[0].is_contiguous():
             dist.all_reduce(ts[0], group=self.group)
             return
@@ -278,6 +291,7 @@ class Comm:
         K = Kmod
         w, b, rank = self.world, self.block, self.rank
         buf, peers = st.buffer(k)
+        self._fence_reuse(st, k)
         n_loc = x_local.shape[0]
         own = buf[:n_loc]
         if x_local.data_ptr() != own.data_ptr():
@@ -316,6 +330,7 @@ class Comm:
         K.wait_flags(flags[1:])
         flags.zero_()
         main.wait_event(done)
+        self._last_use[k] = self._coll_seq
         return y
 
 
