@@ -24,7 +24,8 @@ referenced by some local row, so the halo of a rank IS the other ranks' blocks; 
              carries the rows' fp32 partial sums forward.  (A single kernel that waits inside each row, `sgf_spmm_flagged`,
              is correct but overlaps nothing: every warp stalls in its FIRST row until the last slot has landed - measured
              5.7 ms vs 4.9 ms of pure gather at 2 GPUs; kept as SGF_C4_MODE=push-flagged.)  The consumer lowers its flags after the
-             SpMM; the step's collectives (C1 / C5) order the reuse of a buffer between steps.
+             SpMM; the step's collectives (C1 / C3 / C5) order the reuse of a buffer between steps, and a schedule that has none
+             between two uses of a buffer gets a 4-byte all-reduce as a fence (`Comm._fence_reuse`).
   rotated    the same rotated layout filled by one all-gather (CPU tests of the layout; no overlap).
   allgather  r1 behaviour: blocking all-gather of the blocks in rank order, plain SpMM.
 """
