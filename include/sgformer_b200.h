@@ -96,6 +96,10 @@ int sgf_remove_self_loops(const int64_t* edge_index, int64_t nnz, int64_t* out_e
                           void* ws, size_t ws_bytes, void* stream);
 int sgf_add_self_loops(const int64_t* edge_index, int64_t nnz, int64_t n, int64_t* out_edge_index /* [2, nnz+n], pitch nnz+n */,
                        void* stream);
+/* Is the edge multiset symmetric ({(r,c)} == {(c,r)})?  out2[0], out2[1] (device) receive order-independent 64-bit hash sums of
+ * the two multisets; equal sums <=> symmetric (2^-64 collision odds).  One pass over edge_index.  Decides whether the backward
+ * SpMM (A^T, autograd of torch_sparse.matmul, large/ours.py:33) can reuse the forward CSR. */
+int sgf_edge_symmetry(const int64_t* edge_index, int64_t nnz, int64_t n, uint64_t* out2, void* stream);
 /* K9 on the CSR: the induced subgraph of `subset` emitted directly as the subset's own CSR (rows = subset order, columns
  * = positions in subset, sorted; dinv from the induced in-degrees) — the structure GraphConv needs for a mini-batch, in
  * O(sum of the subset rows' lengths) instead of PyG subgraph's O(E) mask per batch + a CSR rebuild.

@@ -92,6 +92,7 @@ _SIGS = {
     "sgf_csr_build_rect": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sgf_subgraph_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "sgf_to_undirected_ws_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
+    "sgf_edge_symmetry": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "sgf_to_undirected": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "sgf_remove_self_loops_ws_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
     "sgf_remove_self_loops": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),

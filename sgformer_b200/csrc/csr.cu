@@ -12,6 +12,8 @@
 //             in global memory above) so the arrays are deterministic and bit-exact with the reference's
 //             (target, source)-sorted storage
 //   dinv    : dinv[i] = sqrt(1/len_i) (0 for empty rows)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch_count.h"
 #include "../../include/sgformer_b200.h"
@@ -126,15 +128,19 @@ __global__ void scan_add_kernel(int64_t* __restrict__ rowptr, int64_t n, const i
     }
 }
 
-__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz, int64_t shard_begin,
                                 int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
                                 const int64_t* __restrict__ rowptr, int* __restrict__ cursor, int32_t* __restrict__ col) {
+    // [row_begin, row_end) is the row window of THIS launch (sgf_csr_build_rot runs one launch per window so that the scattered
+    // 4-byte writes of a launch stay inside an L2-sized piece of `col`); rowptr / cursor are indexed relative to shard_begin.
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        int64_t k = key[e], v = val[e];
-        if (k < row_begin || k >= row_end || v < 0 || v >= n_cols) continue;
+        int64_t k = key[e];
+        if (k < row_begin || k >= row_end) continue;
+        int64_t v = val[e];
+        if (v < 0 || v >= n_cols) continue;
         if (drop_self_loops && k == v) continue;
-        k -= row_begin;
+        k -= shard_begin;
         int pos = atomicAdd(&cursor[k], 1);
         col[rowptr[k] + pos] = (int32_t)v;
     }
@@ -229,7 +235,26 @@ __global__ void __launch_bounds__(256) csr_sort_rows_warp_kernel(const int64_t* 
             if (lane < len) col[s + rank] = v;  // all reads completed above (shuffles are warp-synchronous)
             continue;
         }
-        int p2 = 64;
+        if (len <= 64) {
+            // two entries per lane (indices lane, lane + 32), ranks from 64 shuffles: ~3x fewer instructions than the bitonic network
+            // for the 33..64-entry rows that make up graphs of mean degree ~50.  Ties are ordered by index, so ranks are distinct.
+            const int32_t v0 = col[s + lane];
+            const int32_t v1 = lane + 32 < len ? col[s + lane + 32] : INT32_MAX;
+            int r0 = 0, r1 = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int32_t a = __shfl_sync(0xffffffffu, v0, j);      // entry j
+                const int32_t b = __shfl_sync(0xffffffffu, v1, j);      // entry j + 32
+                r0 += (a < v0) || (a == v0 && j < lane);
+                r0 += (b < v0);
+                r1 += (a <= v1);
+                r1 += (b < v1) || (b == v1 && j < lane);
+            }
+            col[s + r0] = v0;                            // every lane has read its entries before the first write
+            if (lane + 32 < len) col[s + r1] = v1;
+            continue;
+        }
+        int p2 = 128;
         while (p2 < len) p2 <<= 1;
         for (int i = lane; i < p2; i += 32) sm[i] = i < len ? col[s + i] : INT32_MAX;
         __syncwarp();
@@ -474,6 +499,38 @@ __global__ void __launch_bounds__(256) row_unique_emit_kernel(const int64_t* __r
     }
 }
 
+// Order-independent 64-bit hash sums of {(r,c)} and {(c,r)}: equal sums <=> the edge multiset is symmetric (up to a 2^-64 collision).
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 29;
+    x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
+    x *= 0x94D049BB133111EBULL; x ^= x >> 31;
+    return x;
+}
+__global__ void __launch_bounds__(256) edge_symmetry_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t nnz,
+                                                            uint64_t n, unsigned long long* __restrict__ out) {
+    uint64_t h1 = 0, h2 = 0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        const uint64_t r = (uint64_t)src[e], c = (uint64_t)dst[e];
+        h1 += mix64(r * n + c);
+        h2 += mix64(c * n + r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+        h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+    }
+    __shared__ uint64_t sm[2][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sm[0][w] = h1; sm[1][w] = h2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        uint64_t t = 0;
+        for (int i = 0; i < 8; ++i) t += sm[threadIdx.x][i];
+        atomicAdd(&out[threadIdx.x], (unsigned long long)t);
+    }
+}
+
 static inline int grid_for(int64_t work, int block, int per_sm = 8) {
     int64_t g = (work + block - 1) / block;
     int64_t cap = (int64_t)num_sms() * per_sm;
@@ -483,6 +540,17 @@ static inline int grid_for(int64_t work, int block, int per_sm = 8) {
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Row-window size of the CSR fill in bytes of `col` (SGF_CSR_FILL_WINDOW_MB, 0 = one launch); at most kMaxFillWindows launches, so
+// beyond kMaxFillWindows x window bytes the windows simply grow.
+static constexpr int64_t kMaxFillWindows = 12;
+static inline int64_t fill_window_bytes() {
+    static const int64_t v = [] {
+        const char* e = std::getenv("SGF_CSR_FILL_WINDOW_MB");
+        return (int64_t)(e ? std::atoi(e) : 48) << 20;
+    }();
+    return v;
+}
 
 // exclusive scan of int counts (+add) into int64 out[0..n], using block_sums scratch
 static int launch_scan(const int* counts, int64_t n, int add_loop, int64_t* rowptr, int64_t* block_sums,
@@ -592,8 +660,21 @@ extern "C" int sgf_csr_build_rot(const int64_t* edge_index, int64_t nnz, int64_t
     int rc = launch_scan(w.counts, n, self_loop_mode, rowptr, w.block_sums, w.total, w.cursor, st);
     if (rc) return rc;
     if (nnz > 0) {
-        csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, rowptr, w.cursor, col);
-        SGF_LAUNCH_CHECK(); count_launch();
+        // The fill scatters 4-byte entries over `col`; when `col` is much larger than the L2 every write is a DRAM sector
+        // read-modify-write (5.7 ms for the 124 M edges of the products shape).  Row windows whose share of `col` fits the L2 turn
+        // them into L2 hits written back as whole lines, at the price of re-reading the keys once per window.
+        const int64_t win_bytes = fill_window_bytes();
+        int64_t nwin = win_bytes > 0 ? ((nnz + n) * 4 + win_bytes - 1) / win_bytes : 1;
+        if (nwin > kMaxFillWindows) nwin = kMaxFillWindows;
+        if (nwin < 1 || n == 0) nwin = 1;
+        const int64_t rows_per = (n + nwin - 1) / nwin;
+        for (int64_t wi = 0; wi < nwin; ++wi) {
+            const int64_t lo = row_begin + wi * rows_per, hi = lo + rows_per < row_end ? lo + rows_per : row_end;
+            if (nwin > 1 && lo >= hi) break;
+            csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, nwin > 1 ? lo : row_begin, nwin > 1 ? hi : row_end,
+                                                               n_cols, self_loop_mode, rowptr, w.cursor, col);
+            SGF_LAUNCH_CHECK(); count_launch();
+        }
     }
     if (self_loop_mode == 1 && n > 0) {
         csr_add_loops_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, row_begin, rowptr, w.cursor, col);
@@ -818,15 +899,26 @@ extern "C" int sgf_to_undirected(const int64_t* edge_index, int64_t nnz, int64_t
     SGF_LAUNCH_CHECK(); count_launch();
     int rc = launch_scan(w.counts, n, 0, u.rowptr, w.block_sums, w.total, w.cursor, st);
     if (rc) return rc;
-    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(row, colv, nnz, 0, n, n, 0, u.rowptr, w.cursor, u.col);
+    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(row, colv, nnz, 0, 0, n, n, 0, u.rowptr, w.cursor, u.col);
     SGF_LAUNCH_CHECK(); count_launch();
-    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(colv, row, nnz, 0, n, n, 0, u.rowptr, w.cursor, u.col);
+    csr_fill_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(colv, row, nnz, 0, 0, n, n, 0, u.rowptr, w.cursor, u.col);
     SGF_LAUNCH_CHECK(); count_launch();
     if ((rc = sort_rows(u.rowptr, u.col, n, w, st))) return rc;
     row_unique_count_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(u.rowptr, u.col, n, u.ucount);
     SGF_LAUNCH_CHECK(); count_launch();
     if ((rc = launch_scan(u.ucount, n, 0, u.uptr, u.block_sums2, out_count, u.ucursor, st))) return rc;
     row_unique_emit_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(u.rowptr, u.col, n, u.uptr, out_edge_index, 2 * nnz);
+    SGF_LAUNCH_CHECK(); count_launch();
+    return SGF_OK;
+}
+
+extern "C" int sgf_edge_symmetry(const int64_t* edge_index, int64_t nnz, int64_t n, uint64_t* out2, void* stream) {
+    if (nnz < 0 || n < 0 || !out2 || (nnz > 0 && !edge_index)) return SGF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGF_CUDA_TRY(cudaMemsetAsync(out2, 0, 16, st));
+    if (nnz == 0) return SGF_OK;
+    edge_symmetry_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(edge_index, edge_index + nnz, nnz, (uint64_t)n,
+                                                            reinterpret_cast<unsigned long long*>(out2));
     SGF_LAUNCH_CHECK(); count_launch();
     return SGF_OK;
 }

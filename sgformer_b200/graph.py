@@ -14,20 +14,6 @@ from . import kernels as K
 Tensor = torch.Tensor
 
 
-def _is_symmetric(edge_index: Tensor, n: int) -> bool:
-    """Multiset equality of {(r,c)} and {(c,r)} through an order-independent 64-bit hash sum (one device sync)."""
-    r, c = edge_index[0], edge_index[1]
-    k1, k2 = r * n + c, c * n + r
-
-    def hsum(k):
-        x = k * -7046029254386353131          # 0x9E3779B97F4A7C15 as int64, wraps
-        x = x ^ (x >> 29)
-        x = x * -4658895280553007687          # 0xBF58476D1CE4E5B9
-        return (x ^ (x >> 32)).sum()
-
-    return bool((hsum(k1) == hsum(k2)).item())
-
-
 class Graph:
     """rowptr int64 [n_rows+1], col int32 [nnz] (rows = edge targets, sorted columns, duplicates kept), dinv fp32 [n_rows].
     self_loop_mode 0: large/100M GraphConv; 1: PyG gcn_norm (medium GCN).
@@ -91,7 +77,7 @@ class Graph:
         """CSR of the transposed pattern (rows = edge sources) for the backward SpMM; shares storage when the edge
         list is symmetric (the usual case after to_undirected)."""
         if self._t is None:
-            if _is_symmetric(self.edge_index, self.n):
+            if K.edge_symmetry(self.edge_index, self.n):
                 self._t = (self.rowptr, self.col)      # also true per row shard: rows r0..r1 of A^T == rows of A
                 self.heavy_t = self.heavy
             else:

@@ -144,6 +144,15 @@ def _edge_index(edge_index: Tensor) -> Tensor:
     return edge_index.contiguous()
 
 
+def edge_symmetry(edge_index: Tensor, n: int) -> bool:
+    """Multiset equality of {(r,c)} and {(c,r)} (order-independent 64-bit hash sums, one pass, one device sync)."""
+    ei = _edge_index(edge_index)
+    out = torch.empty(2, dtype=torch.int64, device=ei.device)
+    check(lib().sgf_edge_symmetry(_p(ei), ei.shape[1], n, _p(out), _stream()), "sgf_edge_symmetry")
+    a, b = out.tolist()
+    return a == b
+
+
 def to_undirected(edge_index: Tensor, n: int) -> Tensor:
     """K10: PyG to_undirected = every edge in both directions, sorted by (row, col), duplicates removed (bit-exact)."""
     ei = _edge_index(edge_index)

@@ -63,7 +63,7 @@ def _close_gated(a, b, rtol, atol, what, max_bad=3e-5):
 @pytest.mark.parametrize("case", [
     dict(n=1, e=0), dict(n=7, e=0), dict(n=50, e=200), dict(n=300, e=3000, directed=True, isolated=11, dup=57),
     dict(n=2000, e=60000), dict(n=500, e=9000, directed=True, hub=3000), dict(n=1000, e=300, directed=True, hub=280),
-    dict(n=40000, e=400000),
+    dict(n=40000, e=400000), dict(n=1500, e=70000, directed=True, dup=5000),
 ])
 @pytest.mark.parametrize("by_source", [False, True])
 def test_csr_build_bit_exact(K, case, by_source):
@@ -77,6 +77,23 @@ def test_csr_build_bit_exact(K, case, by_source):
     assert np.array_equal(col.cpu().numpy(), cl), "col differs"
     if not by_source:
         assert np.array_equal(dinv.cpu().numpy(), dv), "dinv differs (bitwise)"
+
+
+def test_edge_symmetry(K):
+    """sgf_edge_symmetry: multiset equality of the edge list and its transpose (decides whether the backward SpMM reuses the CSR)."""
+    n = 3000
+    und = rand_graph(n, 40000, 3)
+    assert K.edge_symmetry(und.to(DEV), n)
+    perm = torch.randperm(und.shape[1], generator=torch.Generator().manual_seed(0))
+    assert K.edge_symmetry(und[:, perm].contiguous().to(DEV), n), "order must not matter"
+    d = rand_graph(n, 40000, 3, directed=True)
+    assert not K.edge_symmetry(d.to(DEV), n)
+    k = int((und[0] != und[1]).nonzero()[0])
+    one_more = torch.cat([und, und[:, k:k + 1]], 1)     # (r,c) twice, (c,r) once: same SET, different multiset
+    assert not K.edge_symmetry(one_more.to(DEV), n)
+    loops = torch.cat([und, torch.arange(10).repeat(2, 1)], 1)
+    assert K.edge_symmetry(loops.to(DEV), n)
+    assert K.edge_symmetry(torch.zeros((2, 0), dtype=torch.int64, device=DEV), n)
 
 
 def test_csr_build_matches_c_oracle(K):
