@@ -146,6 +146,7 @@ def _gcn_flat(gnn, prefix):
 class SGFormer(SGFormerBase):
     """medium/ours.py:179-223: attention branch + an injected GNN (`gnn=`)."""
     variant = "medium"
+    _self_loop_mode = 1
 
     def __init__(self, in_channels, hidden_channels, out_channels, num_layers=2, num_heads=1, alpha=0.5, dropout=0.5,
                  use_bn=True, use_residual=True, use_weight=True, use_graph=True, use_act=False, graph_weight=0.8,

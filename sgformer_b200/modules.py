@@ -261,6 +261,23 @@ class SGFormerBase(_Base):
         self._comm = comm if comm is not None else SINGLE
         return self
 
+    _self_loop_mode = 0       # 1 in the medium variant (PyG gcn_norm adds the missing self loops)
+
+    def prepare_graph(self, edge_index, num_nodes: int, backward: bool = True):
+        """Builds (and caches) the structure forward() derives from `edge_index`: the CSR, its normalisation and, for training,
+        the decision whether the backward SpMM shares it.  forward() does this itself on first sight of an edge_index; calling it
+        ahead of time - e.g. on the copy stream of `HostFeeder(prepare=...)` - takes the graph build off the step's critical path."""
+        if not getattr(self, "use_graph", True):
+            return None
+        comm = self._comm
+        if comm.active:
+            g = get_graph(edge_index, comm.n_global, self._self_loop_mode, rows=comm.rows, col_rot=comm.col_rot)
+        else:
+            g = get_graph(edge_index, num_nodes, self._self_loop_mode)
+        if backward:
+            g.transpose()
+        return g
+
     def _finish_init(self, hidden_channels, out_channels, aggregate):
         if aggregate == "add":
             self.fc = nn.Linear(hidden_channels, out_channels)

@@ -385,3 +385,50 @@ def test_evaluate_on_device_matches_reference_formula():
     ref_loss = torch.nn.functional.nll_loss(lsm[split["valid"]], label.squeeze(1)[split["valid"]]).item()
     assert abs(vloss.item() - ref_loss) < 1e-5
     assert torch.allclose(out.cpu(), lsm, atol=1e-6)
+
+
+def test_host_feeder_prepare_overlaps_graph_build():
+    """get -> step -> submit order with prepare=model.prepare_graph: the CSR of the next batch is built on the copy stream while the
+    current step runs; results equal the plain (build inside forward) loop and every slot is consumed before it is overwritten."""
+    from sgformer_b200 import large as L
+    from sgformer_b200.feed import HostFeeder
+    from sgformer_b200.graph import clear_cache
+    from sgformer_b200.synth import make_graph
+    dev = torch.device("cuda:0")
+    n, d, h, c = 20000, 32, 64, 5
+    kw = dict(gnn_num_layers=2, gnn_dropout=0.0, trans_dropout=0.0)
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for i in range(5):
+        ei = make_graph(n, 80000 + 5000 * i, seed=i)
+        if i == 3:
+            ei = ei[:, ei[0] < ei[1]].contiguous()        # a directed one: the backward needs its own transposed CSR
+        batches.append((torch.randn(n, d, generator=g).pin_memory(), ei.pin_memory(), torch.randint(0, c, (n,), generator=g).pin_memory()))
+
+    def run(prefetch):
+        clear_cache()
+        torch.manual_seed(1)
+        model = L.SGFormer(d, h, c, **kw).to(dev)
+        model.train()
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        feeder = HostFeeder(dev, prepare=(lambda x, ei, y: model.prepare_graph(ei, x.shape[0])) if prefetch else None)
+        feeder.submit(batches[0])
+        losses = []
+        for i in range(len(batches)):
+            x, ei, y = feeder.get()
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(model(x, ei), y)
+            loss.backward()
+            opt.step()
+            if i + 1 < len(batches):
+                feeder.submit(batches[i + 1])
+            losses.append(loss)
+        torch.cuda.synchronize()
+        return torch.stack(losses).cpu(), [p.detach().clone() for p in model.parameters()]
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    # same kernels on the same data; only the order of the float atomics inside the column reductions may differ
+    assert torch.allclose(l0, l1, rtol=1e-5, atol=1e-6), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
