@@ -13,6 +13,13 @@ for l in sys.stdin:
     d=json.loads(l); print('SGF_ATTN_RESIDENT=$R ms/step', d['ms_per_step'], 'spmm', d['roofline']['avg_launch_ms'], 'clk', d['clocks'])"
 done
 for W in 0 32 48 64 96; do SGF_CSR_FILL_WINDOW_MB=$W timeout 200 python scripts/bench_csr.py 2>&1 | tail -n 1; done
+for P in 0 1; do
+  SGF_BENCH_PREPARE=$P timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-extra > $OUT/bench_prepare$P.log 2>&1
+  grep "^{" $OUT/bench_prepare$P.log | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('SGF_BENCH_PREPARE=$P ms/step', d['ms_per_step'], 'e2e', d['e2e'])"
+done
 timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > $OUT/bench_default.log 2>&1; echo "bench rc=$?"
 grep "^{" $OUT/bench_default.log | cut -c1-6000
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gemm_nt_kernel -s 45 -c 15 --csv --log-file $OUT/r2d_gemm_nt_times.csv python bench.py --no-cpu-baseline --no-e2e --no-extra --no-graph --steps 1 --warmup 3 > /dev/null 2>&1; echo "ncu gemm_nt times rc=$?"
