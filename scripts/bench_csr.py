@@ -30,4 +30,4 @@ def timed(fn, reps=5):
 
 t_build = timed(lambda: K.csr_build(ei, n, False, 0, True))
 t_sym = timed(lambda: K.edge_symmetry(ei, n))
-print(f"window_mb={os.environ.get('SGF_CSR_FILL_WINDOW_MB', 'default')} nnz={ei.shape[1]} csr_build {t_build:.3f} ms  edge_symmetry {t_sym:.3f} ms")
+print(f"buckets={os.environ.get('SGF_CSR_BUCKETS', 'default')} window_mb={os.environ.get('SGF_CSR_FILL_WINDOW_MB', 'default')} nnz={ei.shape[1]} csr_build {t_build:.3f} ms  edge_symmetry {t_sym:.3f} ms")
