@@ -205,38 +205,45 @@ __device__ __forceinline__ void bitonic_block(int32_t* a, int npow2, int tid, in
     }
 }
 
-// Ascending sort of col[s, s + len), 2 <= len <= kWarpSortMax, by one warp: <= 32 entries rank-sorted in registers, <= 64 with two
-// entries per lane, longer rows by a bitonic network in `sm` (kWarpSortMax ints of per-warp scratch).
+// Ascending sort of col[s, s + len), 2 <= len <= kWarpSortMax, by one warp: <= 64 entries by a bitonic network in registers (one or
+// two entries per lane, shuffles), longer rows by a bitonic network in `sm` (kWarpSortMax ints of per-warp scratch).
 constexpr int kWarpSortMax = 256;
+// bitonic network over 32 * NREG entries held NREG per lane (entry i = lane + 32 * reg): compare-exchange partners at distance
+// j < 32 by shfl.xor, at distance 32 inside the lane.  ~8 instructions per stage and register instead of the ~9 per ENTRY of a rank sort.
+template <int NREG>
+__device__ __forceinline__ void warp_bitonic(int32_t (&v)[NREG], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * NREG; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {                      // NREG == 2, k == 64: ascending everywhere
+                const int32_t lo = min(v[0], v[NREG - 1]), hi = max(v[0], v[NREG - 1]);
+                v[0] = lo; v[NREG - 1] = hi;
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < NREG; ++r) {
+                    const int32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = ((lane + 32 * r) & k) == 0;
+                    v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void warp_sort_row(int32_t* __restrict__ col, int64_t s, int len, int32_t* sm, int lane) {
     if (len <= 32) {
-        int32_t v = lane < len ? col[s + lane] : INT32_MAX;
-        int rank = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int32_t o = __shfl_sync(0xffffffffu, v, j);
-            rank += (o < v) || (o == v && j < lane);
-        }
-        if (lane < len) col[s + rank] = v;  // all reads completed above (shuffles are warp-synchronous)
+        int32_t v[1] = {lane < len ? col[s + lane] : INT32_MAX};      // padding sorts to the end (column ids are < INT32_MAX)
+        warp_bitonic<1>(v, lane);
+        if (lane < len) col[s + lane] = v[0];
         return;
     }
     if (len <= 64) {
-        // two entries per lane (indices lane, lane + 32), ranks from 64 shuffles: ~3x fewer instructions than the bitonic network
-        // for the 33..64-entry rows that make up graphs of mean degree ~50.  Ties are ordered by index, so ranks are distinct.
-        const int32_t v0 = col[s + lane];
-        const int32_t v1 = lane + 32 < len ? col[s + lane + 32] : INT32_MAX;
-        int r0 = 0, r1 = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int32_t a = __shfl_sync(0xffffffffu, v0, j);      // entry j
-            const int32_t b = __shfl_sync(0xffffffffu, v1, j);      // entry j + 32
-            r0 += (a < v0) || (a == v0 && j < lane);
-            r0 += (b < v0);
-            r1 += (a <= v1);
-            r1 += (b < v1) || (b == v1 && j < lane);
-        }
-        col[s + r0] = v0;                            // every lane has read its entries before the first write
-        if (lane + 32 < len) col[s + r1] = v1;
+        int32_t v[2] = {col[s + lane], lane + 32 < len ? col[s + lane + 32] : INT32_MAX};
+        warp_bitonic<2>(v, lane);
+        col[s + lane] = v[0];
+        if (lane + 32 < len) col[s + lane + 32] = v[1];
         return;
     }
     int p2 = 128;
@@ -537,25 +544,57 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(const int64_t* __rest
         if (hist[i]) atomicAdd(&bucket_cnt[i], (unsigned long long)hist[i]);
 }
 
-// staged[pos] = (row within bucket) << 32 | column id, appended per bucket
-__global__ void __launch_bounds__(256) bucket_scatter_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                                             int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                                             int log_b, unsigned long long* __restrict__ cursor,
-                                                             uint64_t* __restrict__ staged, int* __restrict__ err) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// staged[pos] = (row within bucket) << 32 | column id, appended per bucket.  A block handles tiles of kScatterTile edges: shared-memory
+// histogram of the tile -> ONE global atomic per (tile, bucket) reserves the run -> second pass over the tile (L2 hits) places the
+// entries by shared-memory ranks.  (One global atomic per EDGE on a few thousand hot counters serialises in the L2: 5.2 ms measured
+// for 124 M edges.)
+constexpr int kScatterThreads = 512;
+constexpr int kScatterTile = kScatterThreads * 64;
+__global__ void __launch_bounds__(kScatterThreads) bucket_scatter_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val,
+                                                                         int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
+                                                                         int drop_self_loops, int log_b, int nb,
+                                                                         unsigned long long* __restrict__ cursor,
+                                                                         uint64_t* __restrict__ staged, int* __restrict__ err) {
+    extern __shared__ unsigned long long scatter_sm[];
+    unsigned long long* gb = scatter_sm;                           // [nb] start of this tile's run in bucket b
+    int* hist = reinterpret_cast<int*>(scatter_sm + nb);           // [nb] tile histogram, then the running rank
     const int64_t mask = ((int64_t)1 << log_b) - 1;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        const int64_t k = key[e], v = val[e];
-        if (!edge_ok(k, v, row_begin, row_end, n_cols, drop_self_loops, err)) continue;
-        const int64_t r = k - row_begin;
-        const unsigned long long pos = atomicAdd(&cursor[r >> log_b], 1ull);
-        staged[pos] = ((uint64_t)(r & mask) << 32) | (uint64_t)(uint32_t)v;
+    const int64_t ntiles = (nnz + kScatterTile - 1) / kScatterTile;
+    for (int i = threadIdx.x; i < nb; i += kScatterThreads) hist[i] = 0;
+    __syncthreads();
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t t0 = t * kScatterTile;
+        const int64_t t1 = t0 + kScatterTile < nnz ? t0 + kScatterTile : nnz;
+#pragma unroll 4
+        for (int64_t e = t0 + threadIdx.x; e < t1; e += kScatterThreads) {
+            const int64_t k = key[e], v = val[e];
+            if (edge_ok(k, v, row_begin, row_end, n_cols, drop_self_loops, err)) atomicAdd(&hist[(k - row_begin) >> log_b], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += kScatterThreads) {
+            const int c = hist[i];
+            if (c) gb[i] = atomicAdd(&cursor[i], (unsigned long long)c);
+            hist[i] = 0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int64_t e = t0 + threadIdx.x; e < t1; e += kScatterThreads) {
+            const int64_t k = key[e], v = val[e];
+            if (k < row_begin || k >= row_end || k >= n_cols || v < 0 || v >= n_cols || (drop_self_loops && k == v)) continue;
+            const int64_t r = k - row_begin;
+            const int b = (int)(r >> log_b);
+            const int rank = atomicAdd(&hist[b], 1);
+            staged[gb[b] + rank] = ((uint64_t)(r & mask) << 32) | (uint64_t)(uint32_t)v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += kScatterThreads) hist[i] = 0;
+        __syncthreads();
     }
 }
 
 // One CTA per bucket: per-row counts (shared-memory atomics) -> exclusive scan -> rowptr / dinv -> fill -> (self loops) -> per-row sort.
 // base[b] = edges in front of bucket b (exclusive scan of the bucket counts, base[nb] = total).
-__global__ void __launch_bounds__(kBucketThreads) bucket_build_kernel(const uint64_t* __restrict__ staged, const int64_t* __restrict__ base,
+__global__ void __launch_bounds__(kBucketThreads, 3) bucket_build_kernel(const uint64_t* __restrict__ staged, const int64_t* __restrict__ base,
                                                                       int nb, int log_b, int64_t n, int64_t row_begin, int add_loops,
                                                                       int64_t col_rot, int64_t col_mod, int64_t* __restrict__ rowptr,
                                                                       int32_t* __restrict__ col, float* __restrict__ dinv,
@@ -576,6 +615,7 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_build_kernel(const uint
         const int64_t col_base = e0 + (add_loops ? row0 : 0);      // every bucket in front is full (B rows, one loop each)
         for (int i = tid; i < B; i += nt) cnt[i] = 0;
         __syncthreads();
+#pragma unroll 4
         for (int64_t e = e0 + tid; e < e1; e += nt) atomicAdd(&cnt[(int)(staged[e] >> 32)], 1);
         __syncthreads();
         int local = 0;
@@ -620,6 +660,7 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_build_kernel(const uint
             if (b == nb - 1) rowptr[n] = col_base + excl;
         }
         __syncthreads();
+#pragma unroll 4
         for (int64_t e = e0 + tid; e < e1; e += nt) {
             const uint64_t w = staged[e];
             const int lr = (int)(w >> 32);
@@ -811,6 +852,7 @@ static int build_bucketed(const int64_t* key, const int64_t* val, int64_t nnz, i
     static bool attr_set = false;
     if (!attr_set) {
         SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * 4));
+        SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * 12));
         SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(((size_t)2 * ((size_t)1 << kMaxLogB) + 32 + (size_t)(kBucketThreads / 32) * kWarpSortMax) * 4)));
         attr_set = true;
@@ -822,8 +864,10 @@ static int build_bucketed(const int64_t* key, const int64_t* val, int64_t nnz, i
     scan_block_sums_kernel<<<1, kScanBlock, 0, st>>>(w.bucket_base, nb, w.bucket_base + nb);      // exclusive, total -> base[nb]
     SGF_LAUNCH_CHECK(); count_launch();
     SGF_CUDA_TRY(cudaMemcpyAsync(w.bucket_cursor, w.bucket_base, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
-    bucket_scatter_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, log_b,
-                                                             w.bucket_cursor, w.staged, w.err);
+    const int64_t ntiles = (nnz + kScatterTile - 1) / kScatterTile;
+    const int sgrid = (int)(ntiles < (int64_t)num_sms() * 4 ? ntiles : (int64_t)num_sms() * 4);
+    bucket_scatter_kernel<<<sgrid, kScatterThreads, (size_t)nb * 12, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, log_b, nb,
+                                                                         w.bucket_cursor, w.staged, w.err);
     SGF_LAUNCH_CHECK(); count_launch();
     int grid = nb < num_sms() * 4 ? nb : num_sms() * 4;
     bucket_build_kernel<<<grid, kBucketThreads, build_bytes, st>>>(w.staged, w.bucket_base, nb, log_b, n, row_begin, self_loop_mode, col_rot,
