@@ -23,17 +23,32 @@ namespace sgf {
 constexpr int kScanBlock = 1024;
 constexpr int kScanItems = 4;  // per thread -> 4096 per block
 
-// rows [row_begin, row_end) of a matrix with n_cols columns are built; edges whose key falls outside are skipped
-__global__ void csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                 int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                 int* __restrict__ counts, int* __restrict__ err) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        int64_t k = key[e], v = val[e];
-        if (k < 0 || k >= n_cols || v < 0 || v >= n_cols) { atomicExch(err, 1); continue; }
-        if (k < row_begin || k >= row_end) continue;
-        if (drop_self_loops && k == v) continue;
-        atomicAdd(&counts[k - row_begin], 1);
+// rows [row_begin, row_end) of a matrix with n_cols columns are built; edges whose key falls outside are skipped.
+// kEdgeUnroll independent 8-byte loads per thread and array are issued before the first use: at one load per thread the edge passes
+// run at 2.4 TB/s (long-scoreboard bound, ncu r2g), a third of what the memory system delivers.
+constexpr int kEdgeUnroll = 4;
+__global__ void __launch_bounds__(256) csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+                                                        int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
+                                                        int* __restrict__ counts, int* __restrict__ err) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < nnz; e0 += stride * kEdgeUnroll) {
+        int64_t k[kEdgeUnroll], v[kEdgeUnroll];
+        bool in[kEdgeUnroll];
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u) {
+            const int64_t e = e0 + u * stride;
+            in[u] = e < nnz;
+            k[u] = in[u] ? key[e] : 0;
+            v[u] = in[u] ? val[e] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u) {
+            if (!in[u]) continue;
+            if (k[u] < 0 || k[u] >= n_cols || v[u] < 0 || v[u] >= n_cols) { atomicExch(err, 1); continue; }
+            if (k[u] < row_begin || k[u] >= row_end) continue;
+            if (drop_self_loops && k[u] == v[u]) continue;
+            atomicAdd(&counts[k[u] - row_begin], 1);
+        }
     }
 }
 
@@ -128,21 +143,40 @@ __global__ void scan_add_kernel(int64_t* __restrict__ rowptr, int64_t n, const i
     }
 }
 
-__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz, int64_t shard_begin,
-                                int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                const int64_t* __restrict__ rowptr, int* __restrict__ cursor, int32_t* __restrict__ col) {
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+                                                       int64_t shard_begin, int64_t row_begin, int64_t row_end, int64_t n_cols,
+                                                       int drop_self_loops, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
+                                                       int32_t* __restrict__ col) {
     // [row_begin, row_end) is the row window of THIS launch (sgf_csr_build_rot runs one launch per window so that the scattered
     // 4-byte writes of a launch stay inside an L2-sized piece of `col`); rowptr / cursor are indexed relative to shard_begin.
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        int64_t k = key[e];
-        if (k < row_begin || k >= row_end) continue;
-        int64_t v = val[e];
-        if (v < 0 || v >= n_cols) continue;
-        if (drop_self_loops && k == v) continue;
-        k -= shard_begin;
-        int pos = atomicAdd(&cursor[k], 1);
-        col[rowptr[k] + pos] = (int32_t)v;
+    // Stages of kEdgeUnroll independent memory operations each: keys -> values of the keys inside the window -> cursor atomics +
+    // row offsets -> stores.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < nnz; e0 += stride * kEdgeUnroll) {
+        int64_t k[kEdgeUnroll], v[kEdgeUnroll];
+        bool take[kEdgeUnroll];
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u) {
+            const int64_t e = e0 + u * stride;
+            k[u] = e < nnz ? key[e] : -1;
+            take[u] = k[u] >= row_begin && k[u] < row_end;
+        }
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u) {
+            v[u] = take[u] ? val[e0 + u * stride] : -1;
+            take[u] = take[u] && v[u] >= 0 && v[u] < n_cols && !(drop_self_loops && k[u] == v[u]);
+        }
+        int pos[kEdgeUnroll];
+        int64_t start[kEdgeUnroll];
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u) {
+            const int64_t r = take[u] ? k[u] - shard_begin : 0;
+            pos[u] = take[u] ? atomicAdd(&cursor[r], 1) : 0;
+            start[u] = take[u] ? rowptr[r] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kEdgeUnroll; ++u)
+            if (take[u]) col[start[u] + pos[u]] = (int32_t)v[u];
     }
 }
 
@@ -511,185 +545,6 @@ __global__ void __launch_bounds__(256) row_unique_emit_kernel(const int64_t* __r
     }
 }
 
-// ---- bucketed build (large edge lists) ----------------------------------------------------------------
-// count / fill of the direct build scatter 4-byte entries over the whole `col` array: with random edge order every write is a DRAM
-// sector read-modify-write.  The bucketed build first PARTITIONS the edges by row bucket (2^log_b rows) into a staging array -
-// one append stream per bucket, a few thousand open lines that live in the L2 - and then lets one CTA per bucket count, scan,
-// fill and sort its rows inside a piece of `col` of a few hundred KB.  Results are identical (rows are sorted afterwards).
-constexpr int kBucketThreads = 512;
-constexpr int kMaxBuckets = 16384;          // shared-memory histogram of bucket_count_kernel: 64 KB
-constexpr int kMinLogB = 11, kMaxLogB = 14; // rows per bucket 2048 .. 16384 (two int arrays of that size in shared memory)
-
-__device__ __forceinline__ bool edge_ok(int64_t k, int64_t v, int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                        int* err) {
-    if (k < 0 || k >= n_cols || v < 0 || v >= n_cols) { atomicExch(err, 1); return false; }
-    if (k < row_begin || k >= row_end) return false;
-    return !(drop_self_loops && k == v);
-}
-
-__global__ void __launch_bounds__(256) bucket_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                                           int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                                           int log_b, int nb, unsigned long long* __restrict__ bucket_cnt,
-                                                           int* __restrict__ err) {
-    extern __shared__ int hist[];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-        const int64_t k = key[e], v = val[e];
-        if (edge_ok(k, v, row_begin, row_end, n_cols, drop_self_loops, err)) atomicAdd(&hist[(k - row_begin) >> log_b], 1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += blockDim.x)
-        if (hist[i]) atomicAdd(&bucket_cnt[i], (unsigned long long)hist[i]);
-}
-
-// staged[pos] = (row within bucket) << 32 | column id, appended per bucket.  A block handles tiles of kScatterTile edges: shared-memory
-// histogram of the tile -> ONE global atomic per (tile, bucket) reserves the run -> second pass over the tile (L2 hits) places the
-// entries by shared-memory ranks.  (One global atomic per EDGE on a few thousand hot counters serialises in the L2: 5.2 ms measured
-// for 124 M edges.)
-constexpr int kScatterThreads = 512;
-constexpr int kScatterTile = kScatterThreads * 64;
-__global__ void __launch_bounds__(kScatterThreads) bucket_scatter_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val,
-                                                                         int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
-                                                                         int drop_self_loops, int log_b, int nb,
-                                                                         unsigned long long* __restrict__ cursor,
-                                                                         uint64_t* __restrict__ staged, int* __restrict__ err) {
-    extern __shared__ unsigned long long scatter_sm[];
-    unsigned long long* gb = scatter_sm;                           // [nb] start of this tile's run in bucket b
-    int* hist = reinterpret_cast<int*>(scatter_sm + nb);           // [nb] tile histogram, then the running rank
-    const int64_t mask = ((int64_t)1 << log_b) - 1;
-    const int64_t ntiles = (nnz + kScatterTile - 1) / kScatterTile;
-    for (int i = threadIdx.x; i < nb; i += kScatterThreads) hist[i] = 0;
-    __syncthreads();
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t t0 = t * kScatterTile;
-        const int64_t t1 = t0 + kScatterTile < nnz ? t0 + kScatterTile : nnz;
-#pragma unroll 4
-        for (int64_t e = t0 + threadIdx.x; e < t1; e += kScatterThreads) {
-            const int64_t k = key[e], v = val[e];
-            if (edge_ok(k, v, row_begin, row_end, n_cols, drop_self_loops, err)) atomicAdd(&hist[(k - row_begin) >> log_b], 1);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += kScatterThreads) {
-            const int c = hist[i];
-            if (c) gb[i] = atomicAdd(&cursor[i], (unsigned long long)c);
-            hist[i] = 0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int64_t e = t0 + threadIdx.x; e < t1; e += kScatterThreads) {
-            const int64_t k = key[e], v = val[e];
-            if (k < row_begin || k >= row_end || k >= n_cols || v < 0 || v >= n_cols || (drop_self_loops && k == v)) continue;
-            const int64_t r = k - row_begin;
-            const int b = (int)(r >> log_b);
-            const int rank = atomicAdd(&hist[b], 1);
-            staged[gb[b] + rank] = ((uint64_t)(r & mask) << 32) | (uint64_t)(uint32_t)v;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += kScatterThreads) hist[i] = 0;
-        __syncthreads();
-    }
-}
-
-// One CTA per bucket: per-row counts (shared-memory atomics) -> exclusive scan -> rowptr / dinv -> fill -> (self loops) -> per-row sort.
-// base[b] = edges in front of bucket b (exclusive scan of the bucket counts, base[nb] = total).
-__global__ void __launch_bounds__(kBucketThreads, 3) bucket_build_kernel(const uint64_t* __restrict__ staged, const int64_t* __restrict__ base,
-                                                                      int nb, int log_b, int64_t n, int64_t row_begin, int add_loops,
-                                                                      int64_t col_rot, int64_t col_mod, int64_t* __restrict__ rowptr,
-                                                                      int32_t* __restrict__ col, float* __restrict__ dinv,
-                                                                      int64_t* __restrict__ long_rows, int* __restrict__ n_long) {
-    extern __shared__ int smem[];
-    const int B = 1 << log_b;
-    int* cnt = smem;                    // [B]   entries per row, counted down to 0 by the fill
-    int* off = smem + B;                // [B+1] exclusive scan of (cnt + self loop)
-    int32_t* sort_sm = smem + 2 * B + 32;   // [warps][kWarpSortMax]
-    __shared__ int warp_tot[kBucketThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int nt = kBucketThreads, nw = kBucketThreads / 32;
-    const int per = B / nt;             // B >= 2048 > nt: consecutive rows per thread in the scan
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        const int64_t row0 = (int64_t)b << log_b;                  // first row of the bucket (relative to row_begin)
-        const int rows = (int)((n - row0) < B ? (n - row0) : B);
-        const int64_t e0 = base[b], e1 = base[b + 1];
-        const int64_t col_base = e0 + (add_loops ? row0 : 0);      // every bucket in front is full (B rows, one loop each)
-        for (int i = tid; i < B; i += nt) cnt[i] = 0;
-        __syncthreads();
-#pragma unroll 4
-        for (int64_t e = e0 + tid; e < e1; e += nt) atomicAdd(&cnt[(int)(staged[e] >> 32)], 1);
-        __syncthreads();
-        int local = 0;
-        for (int i = 0; i < per; ++i) {
-            const int r = tid * per + i;
-            local += cnt[r] + ((add_loops && r < rows) ? 1 : 0);
-        }
-        int x = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int w = lane < nw ? warp_tot[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            if (lane < nw) warp_tot[lane] = w;      // inclusive over warps
-        }
-        __syncthreads();
-        int excl = x - local + (wid > 0 ? warp_tot[wid - 1] : 0);
-        for (int i = 0; i < per; ++i) {
-            const int r = tid * per + i;
-            const int len = cnt[r] + ((add_loops && r < rows) ? 1 : 0);
-            off[r] = excl;
-            if (r < rows) {
-                rowptr[row0 + r] = col_base + excl;
-                if (dinv) {
-                    const float d = (float)len;
-                    dinv[row0 + r] = d > 0.f ? sqrtf(1.0f / d) : 0.0f;      // as csr_dinv_kernel
-                }
-            }
-            excl += len;
-        }
-        if (tid == nt - 1) {
-            off[B] = excl;
-            if (b == nb - 1) rowptr[n] = col_base + excl;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int64_t e = e0 + tid; e < e1; e += nt) {
-            const uint64_t w = staged[e];
-            const int lr = (int)(w >> 32);
-            int64_t v = (int64_t)(uint32_t)w;
-            if (col_mod > 0) { v -= col_rot; if (v < 0) v += col_mod; }
-            const int p = atomicSub(&cnt[lr], 1) - 1;
-            col[col_base + off[lr] + p] = (int32_t)v;
-        }
-        if (add_loops) {
-            for (int r = tid; r < rows; r += nt) {
-                int64_t v = row_begin + row0 + r;
-                if (col_mod > 0) { v -= col_rot; if (v < 0) v += col_mod; }
-                col[col_base + off[r + 1] - 1] = (int32_t)v;     // last slot of the row: the edges fill slots 0 .. count-1
-            }
-        }
-        __syncthreads();            // the bucket's piece of col is complete (and visible to the block)
-        for (int r = wid; r < rows; r += nw) {
-            const int len = off[r + 1] - off[r];
-            if (len <= 1) continue;
-            if (len > kWarpSortMax) {
-                if (lane == 0) long_rows[atomicAdd(n_long, 1)] = row0 + r;
-                continue;
-            }
-            warp_sort_row(col, col_base + off[r], len, sort_sm + wid * kWarpSortMax, lane);
-        }
-        __syncthreads();
-    }
-}
-
 // Order-independent 64-bit hash sums of {(r,c)} and {(c,r)}: equal sums <=> the edge multiset is symmetric (up to a 2^-64 collision).
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 29;
@@ -767,7 +622,6 @@ using namespace sgf;
 struct CsrWs {
     int* counts; int* cursor; int64_t* block_sums; int64_t* total; int* err; int* n_long;
     unsigned long long* maxlen; int64_t* long_rows; int32_t* scratch; int64_t scratch_elems;
-    uint64_t* staged; int64_t* bucket_base; unsigned long long* bucket_cursor;      // bucketed build only (staged == nullptr otherwise)
     size_t bytes;
 };
 static constexpr int kHubBlocks = 16;
@@ -775,7 +629,7 @@ static constexpr int kHubBlocks = 16;
 // in fill order — still a valid CSR for the SpMM, but not bit-comparable.
 static constexpr int64_t kHubScratchMax = (int64_t)1 << 26;
 
-static CsrWs carve_ws(void* ws, int64_t nnz, int64_t n, bool with_staging = false) {
+static CsrWs carve_ws(void* ws, int64_t nnz, int64_t n) {
     CsrWs w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -795,11 +649,6 @@ static CsrWs carve_ws(void* ws, int64_t nnz, int64_t n, bool with_staging = fals
     w.total = (int64_t*)(base + o_misc); w.err = (int*)(base + o_misc + 8); w.n_long = (int*)(base + o_misc + 12);
     w.maxlen = (unsigned long long*)(base + o_misc + 16);
     w.long_rows = (int64_t*)(base + o_long); w.scratch = (int32_t*)(base + o_scr); w.scratch_elems = p2;
-    w.staged = nullptr; w.bucket_base = nullptr; w.bucket_cursor = nullptr;
-    if (with_staging) {
-        size_t o_bb = take((size_t)(kMaxBuckets + 1) * 8), o_bc = take((size_t)kMaxBuckets * 8), o_st = take((size_t)(nnz > 0 ? nnz : 1) * 8);
-        w.bucket_base = (int64_t*)(base + o_bb); w.bucket_cursor = (unsigned long long*)(base + o_bc); w.staged = (uint64_t*)(base + o_st);
-    }
     w.bytes = off;
     return w;
 }
@@ -827,53 +676,8 @@ static int sort_long_rows(const int64_t* rowptr, int32_t* col, const CsrWs& w, c
 
 extern "C" int sgf_csr_build_ws_bytes(int64_t nnz, int64_t n, size_t* bytes) {
     if (!bytes || nnz < 0 || n < 0) return SGF_ERR_ARG;
-    *bytes = carve_ws(nullptr, nnz, n, true).bytes;
+    *bytes = carve_ws(nullptr, nnz, n).bytes;
     return SGF_OK;
-}
-
-// SGF_CSR_BUCKETS: 0 = direct build only, 1 (default) = bucketed build for edge lists of >= 2^20 entries, 2 = whenever possible
-static inline int bucket_mode() {
-    const char* e = std::getenv("SGF_CSR_BUCKETS");
-    return e ? std::atoi(e) : 1;
-}
-
-// The bucketed build of rows [row_begin, row_end); returns SGF_OK, or -1 when the shape does not fit (caller falls back).
-static int build_bucketed(const int64_t* key, const int64_t* val, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
-                          int self_loop_mode, int64_t col_rot, int64_t col_mod, int64_t* rowptr, int32_t* col, float* dinv,
-                          const CsrWs& w, cudaStream_t st) {
-    const int64_t n = row_end - row_begin;
-    int log_b = kMinLogB;
-    while (log_b < kMaxLogB && ((n + ((int64_t)1 << log_b) - 1) >> log_b) > kMaxBuckets) ++log_b;
-    const int64_t nb64 = (n + ((int64_t)1 << log_b) - 1) >> log_b;
-    if (nb64 < 1 || nb64 > kMaxBuckets || !w.staged) return -1;
-    const int nb = (int)nb64;
-    const size_t hist_bytes = (size_t)nb * 4;
-    const size_t build_bytes = ((size_t)2 * ((size_t)1 << log_b) + 32 + (size_t)(kBucketThreads / 32) * kWarpSortMax) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * 4));
-        SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * 12));
-        SGF_CUDA_TRY(cudaFuncSetAttribute(bucket_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(((size_t)2 * ((size_t)1 << kMaxLogB) + 32 + (size_t)(kBucketThreads / 32) * kWarpSortMax) * 4)));
-        attr_set = true;
-    }
-    SGF_CUDA_TRY(cudaMemsetAsync(w.bucket_base, 0, (size_t)(nb + 1) * 8, st));
-    bucket_count_kernel<<<grid_for(nnz, 256, 4), 256, hist_bytes, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, log_b, nb,
-                                                                      reinterpret_cast<unsigned long long*>(w.bucket_base), w.err);
-    SGF_LAUNCH_CHECK(); count_launch();
-    scan_block_sums_kernel<<<1, kScanBlock, 0, st>>>(w.bucket_base, nb, w.bucket_base + nb);      // exclusive, total -> base[nb]
-    SGF_LAUNCH_CHECK(); count_launch();
-    SGF_CUDA_TRY(cudaMemcpyAsync(w.bucket_cursor, w.bucket_base, (size_t)nb * 8, cudaMemcpyDeviceToDevice, st));
-    const int64_t ntiles = (nnz + kScatterTile - 1) / kScatterTile;
-    const int sgrid = (int)(ntiles < (int64_t)num_sms() * 4 ? ntiles : (int64_t)num_sms() * 4);
-    bucket_scatter_kernel<<<sgrid, kScatterThreads, (size_t)nb * 12, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, log_b, nb,
-                                                                         w.bucket_cursor, w.staged, w.err);
-    SGF_LAUNCH_CHECK(); count_launch();
-    int grid = nb < num_sms() * 4 ? nb : num_sms() * 4;
-    bucket_build_kernel<<<grid, kBucketThreads, build_bytes, st>>>(w.staged, w.bucket_base, nb, log_b, n, row_begin, self_loop_mode, col_rot,
-                                                                  col_mod, rowptr, col, dinv, w.long_rows, w.n_long);
-    SGF_LAUNCH_CHECK(); count_launch();
-    return sort_long_rows(rowptr, col, w, st);
 }
 
 extern "C" int sgf_csr_build_rect(const int64_t* edge_index, int64_t nnz, int64_t row_begin, int64_t row_end, int64_t n_cols,
@@ -893,17 +697,12 @@ extern "C" int sgf_csr_build_rot(const int64_t* edge_index, int64_t nnz, int64_t
     if (col_mod != 0 && (col_mod < n_cols || col_mod >= (int64_t)INT32_MAX || col_rot < 0 || col_rot >= col_mod)) return SGF_ERR_ARG;
     if (nnz > 0 && !edge_index) return SGF_ERR_ARG;
     if (self_loop_mode != 0 && self_loop_mode != 1) return SGF_ERR_ARG;
-    CsrWs w = carve_ws(ws, nnz, n, true);
+    CsrWs w = carve_ws(ws, nnz, n);
     if (ws_bytes < w.bytes) return SGF_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t* key = by_source ? edge_index : edge_index + nnz;
     const int64_t* val = by_source ? edge_index + nnz : edge_index;
     SGF_CUDA_TRY(cudaMemsetAsync(w.total, 0, 64, st));
-    const int bm = bucket_mode();
-    if (n > 0 && nnz > 0 && (bm >= 2 || (bm == 1 && nnz >= ((int64_t)1 << 20)))) {
-        int rb = build_bucketed(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, col_rot, col_mod, rowptr, col, dinv, w, st);
-        if (rb >= 0) return rb;
-    }
     SGF_CUDA_TRY(cudaMemsetAsync(w.counts, 0, (size_t)(n + 1) * 4, st));
     if (nnz > 0) {
         csr_count_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(key, val, nnz, row_begin, row_end, n_cols, self_loop_mode, w.counts, w.err);

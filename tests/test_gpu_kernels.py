@@ -79,42 +79,6 @@ def test_csr_build_bit_exact(K, case, by_source):
         assert np.array_equal(dinv.cpu().numpy(), dv), "dinv differs (bitwise)"
 
 
-@pytest.mark.parametrize("case", [
-    dict(n=1, e=3), dict(n=50, e=200), dict(n=2049, e=30000, directed=True, isolated=11, dup=570),
-    dict(n=5000, e=9000, directed=True, hub=3000), dict(n=40000, e=400000), dict(n=70000, e=100000, directed=True, dup=1000, hub=300),
-])
-@pytest.mark.parametrize("mode", ["plain", "by_source", "pyg_loops", "shard", "shard_rot_loops"])
-def test_csr_build_bucketed_equals_direct(K, monkeypatch, case, mode):
-    """The bucketed build (partition by row bucket -> one CTA per bucket: count / scan / fill / sort) is bit-identical to the direct
-    build (global count / scan / scattered fill / sort), which the tests above pin to the reference's storage order."""
-    c = dict(case)
-    n, e = c.pop("n"), c.pop("e")
-    ei = rand_graph(n, e, 5, **c)
-    if mode == "pyg_loops":
-        ei[1, :7] = ei[0, :7]           # explicit self loops: dropped, then one per row added
-    ei = ei.to(DEV)
-    kw = dict(by_source=mode == "by_source", self_loop_mode=1 if "loops" in mode else 0)
-    if mode.startswith("shard"):
-        block = (n + 2) // 3
-        r0, r1 = block, min(n, 2 * block)
-        if r1 <= r0:
-            pytest.skip("graph too small to shard")
-        kw["rows"] = (r0, r1)
-        if "rot" in mode:
-            kw["col_rot"] = (r0, 3 * block)
-
-    def build():
-        return K.csr_build(ei, n, kw["by_source"], kw["self_loop_mode"], True, rows=kw.get("rows"), col_rot=kw.get("col_rot"))
-
-    monkeypatch.setenv("SGF_CSR_BUCKETS", "0")
-    rp0, cl0, dv0 = build()
-    monkeypatch.setenv("SGF_CSR_BUCKETS", "2")
-    rp1, cl1, dv1 = build()
-    assert torch.equal(rp0, rp1), "rowptr differs"
-    assert torch.equal(cl0, cl1), "col differs"
-    assert (dv0 is None and dv1 is None) or torch.equal(dv0, dv1), "dinv differs"
-
-
 def test_edge_symmetry(K):
     """sgf_edge_symmetry: multiset equality of the edge list and its transpose (decides whether the backward SpMM reuses the CSR)."""
     n = 3000
