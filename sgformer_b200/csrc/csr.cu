@@ -24,31 +24,17 @@ constexpr int kScanBlock = 1024;
 constexpr int kScanItems = 4;  // per thread -> 4096 per block
 
 // rows [row_begin, row_end) of a matrix with n_cols columns are built; edges whose key falls outside are skipped.
-// kEdgeUnroll independent 8-byte loads per thread and array are issued before the first use: at one load per thread the edge passes
-// run at 2.4 TB/s (long-scoreboard bound, ncu r2g), a third of what the memory system delivers.
-constexpr int kEdgeUnroll = 4;
-__global__ void __launch_bounds__(256) csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                                        int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
-                                                        int* __restrict__ counts, int* __restrict__ err) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < nnz; e0 += stride * kEdgeUnroll) {
-        int64_t k[kEdgeUnroll], v[kEdgeUnroll];
-        bool in[kEdgeUnroll];
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u) {
-            const int64_t e = e0 + u * stride;
-            in[u] = e < nnz;
-            k[u] = in[u] ? key[e] : 0;
-            v[u] = in[u] ? val[e] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u) {
-            if (!in[u]) continue;
-            if (k[u] < 0 || k[u] >= n_cols || v[u] < 0 || v[u] >= n_cols) { atomicExch(err, 1); continue; }
-            if (k[u] < row_begin || k[u] >= row_end) continue;
-            if (drop_self_loops && k[u] == v[u]) continue;
-            atomicAdd(&counts[k[u] - row_begin], 1);
-        }
+// (ncu r2g/r2h: 0.86 ms for 124 M edges = the L2's atomic rate; issuing four independent loads per thread changes nothing.)
+__global__ void csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
+                                 int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
+                                 int* __restrict__ counts, int* __restrict__ err) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        int64_t k = key[e], v = val[e];
+        if (k < 0 || k >= n_cols || v < 0 || v >= n_cols) { atomicExch(err, 1); continue; }
+        if (k < row_begin || k >= row_end) continue;
+        if (drop_self_loops && k == v) continue;
+        atomicAdd(&counts[k - row_begin], 1);
     }
 }
 
@@ -143,40 +129,21 @@ __global__ void scan_add_kernel(int64_t* __restrict__ rowptr, int64_t n, const i
     }
 }
 
-__global__ void __launch_bounds__(256) csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz,
-                                                       int64_t shard_begin, int64_t row_begin, int64_t row_end, int64_t n_cols,
-                                                       int drop_self_loops, const int64_t* __restrict__ rowptr, int* __restrict__ cursor,
-                                                       int32_t* __restrict__ col) {
+__global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t nnz, int64_t shard_begin,
+                                int64_t row_begin, int64_t row_end, int64_t n_cols, int drop_self_loops,
+                                const int64_t* __restrict__ rowptr, int* __restrict__ cursor, int32_t* __restrict__ col) {
     // [row_begin, row_end) is the row window of THIS launch (sgf_csr_build_rot runs one launch per window so that the scattered
     // 4-byte writes of a launch stay inside an L2-sized piece of `col`); rowptr / cursor are indexed relative to shard_begin.
-    // Stages of kEdgeUnroll independent memory operations each: keys -> values of the keys inside the window -> cursor atomics +
-    // row offsets -> stores.
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < nnz; e0 += stride * kEdgeUnroll) {
-        int64_t k[kEdgeUnroll], v[kEdgeUnroll];
-        bool take[kEdgeUnroll];
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u) {
-            const int64_t e = e0 + u * stride;
-            k[u] = e < nnz ? key[e] : -1;
-            take[u] = k[u] >= row_begin && k[u] < row_end;
-        }
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u) {
-            v[u] = take[u] ? val[e0 + u * stride] : -1;
-            take[u] = take[u] && v[u] >= 0 && v[u] < n_cols && !(drop_self_loops && k[u] == v[u]);
-        }
-        int pos[kEdgeUnroll];
-        int64_t start[kEdgeUnroll];
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u) {
-            const int64_t r = take[u] ? k[u] - shard_begin : 0;
-            pos[u] = take[u] ? atomicAdd(&cursor[r], 1) : 0;
-            start[u] = take[u] ? rowptr[r] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kEdgeUnroll; ++u)
-            if (take[u]) col[start[u] + pos[u]] = (int32_t)v[u];
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        int64_t k = key[e];
+        if (k < row_begin || k >= row_end) continue;
+        int64_t v = val[e];
+        if (v < 0 || v >= n_cols) continue;
+        if (drop_self_loops && k == v) continue;
+        k -= shard_begin;
+        int pos = atomicAdd(&cursor[k], 1);
+        col[rowptr[k] + pos] = (int32_t)v;
     }
 }
 
@@ -593,7 +560,7 @@ static constexpr int64_t kMaxFillWindows = 12;
 static inline int64_t fill_window_bytes() {
     static const int64_t v = [] {
         const char* e = std::getenv("SGF_CSR_FILL_WINDOW_MB");
-        return (int64_t)(e ? std::atoi(e) : 96) << 20;
+        return (int64_t)(e ? std::atoi(e) : 128) << 20;
     }();
     return v;
 }
