@@ -8,8 +8,8 @@ shapes (BASELINE.json).  One JSON line on stdout (rank 0).
 
 Timed region: device-timed with CUDA events on the launching stream, barrier + synchronize on both sides, max over
 ranks.  `value` has the inputs resident in HBM; `e2e` copies the step's inputs from pinned host memory every step
-(through `sgformer_b200.feed.HostFeeder`: step i+1's copy overlaps step i's compute; the CSR is rebuilt from the fresh
-edge_index every step) and reads the loss back.  `roofline` is the CSR SpMM (the dominant kernel): algorithmic
+(through `sgformer_b200.feed.HostFeeder`: step i+1's copy AND the CSR build from its fresh edge_index run on a copy stream
+beside step i - still inside the timed region, every step) and reads the loss back.  `roofline` is the CSR SpMM (the dominant kernel): algorithmic
 bytes per launch / its CUDA-event duration inside the timed steps, against MEASURED_PEAKS.json.
 
 Besides the headline line (BASELINE config 3, dp weak scaling at N > 1) the `extra` block carries the other BASELINE
