@@ -1118,9 +1118,10 @@ using namespace sgf;
         }                                                                                                  \
     } while (0)
 
-// SGF_BN_BWD_RING: shared-memory staging ring in the BatchNorm backward (rows of <= 32 chunks)
+// SGF_BN_BWD_RING (default on): shared-memory staging ring in the BatchNorm backward (rows of <= 32 chunks).  Measured (r2m, same
+// box, products-shaped step): 92.61 ms/step with the register pipeline, 91.39 with the ring; the whole GPU suite passes with it.
 static inline bool bn_bwd_ring() {
-    static const bool v = [] { const char* e = std::getenv("SGF_BN_BWD_RING"); return e ? std::atoi(e) != 0 : false; }();
+    static const bool v = [] { const char* e = std::getenv("SGF_BN_BWD_RING"); return e ? std::atoi(e) != 0 : true; }();
     return v;
 }
 static inline size_t bn_bwd_ring_smem(int h) {
